@@ -1,0 +1,162 @@
+/*
+ * ogmm_b200 -- C ABI of the B200-native OGMM registration hot path.
+ *
+ * One entry point per kernel group of SURVEY.md section 8(b).  Every function
+ *   - takes raw DEVICE pointers, element counts, element strides and a CUDA
+ *     stream handle (a cudaStream_t passed as void*; NULL = legacy default
+ *     stream); no torch types cross this boundary;
+ *   - launches on the CALLER's current device and the given stream, never
+ *     synchronises the device, holds no global mutable state (the last-error
+ *     string is thread-local) -- safe under one-host-thread-per-GPU callers
+ *     such as nn.DataParallel (reference train.py:190-192);
+ *   - returns OGMM_OK (0) or a negative OGMM_E* code and never throws.
+ *
+ * All floating point is fp32, all indices are int64, exactly as in the
+ * reference.  Tensors named (B,N,C) are LOGICAL shapes; where strides are
+ * taken the tensor may be any view (the reference passes transposed views,
+ * models/gmmreg.py:26-27, models/dgcnn.py:135).  Strides are in ELEMENTS.
+ *
+ * The reference is pure Python/PyTorch: it has no FFI of its own.  Each entry
+ * point therefore cites the reference FUNCTION (file:line under the reference
+ * checkout) whose arithmetic it replaces; INTEGRATION.md shows the ctypes stub
+ * and the module-patching a maintainer adds on the reference side.
+ */
+#ifndef OGMM_B200_H_
+#define OGMM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OGMM_ABI_VERSION 1
+
+#define OGMM_OK            0
+#define OGMM_EINVAL       -1   /* bad shape / null pointer / negative size            */
+#define OGMM_EUNSUPPORTED -2   /* k, J, N or C outside what the kernels are built for */
+#define OGMM_ECUDA        -3   /* launch or runtime failure (see ogmm_last_error)     */
+#define OGMM_EWORKSPACE   -4   /* workspace too small                                  */
+
+typedef void* ogmm_stream_t;
+
+/* ABI version of the loaded library (== OGMM_ABI_VERSION). */
+int ogmm_version(void);
+/* Thread-local description of the last non-zero status returned on this thread. */
+const char* ogmm_last_error(void);
+/* SM count and compute capability of the current device (any pointer may be NULL). */
+int ogmm_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- K1: fused pairwise distance + per-row top-k (+ edge gather) --------------------------
+ * Replaces lib/utils.py:12-34 square_distance, :37-44 knn and, when `edge` is non-NULL,
+ * :47-66 get_graph_feature (the models/dgcnn.py:135-137 call pair).
+ *   src (B,N,C), dst (B,M,C): strided views.   idx_out (B,N,k) int64 contiguous: the k smallest
+ *   expanded-form squared distances per row, ascending, ties -> lowest index.
+ *   normalize != 0 selects the cosine form 2 - 2 s.d (lib/utils.py:29-30).
+ *   edge_out (optional; requires dst == src cloud, i.e. a self graph): (B,N,k,2C) contiguous
+ *   memory holding [x_j - x_i ; x_i]; the reference's (B,2C,N,k) result is the permuted view.
+ *   dist_out (optional): (B,N,k) the selected distances.
+ * C == 3 uses the specialised FP32 kernel; other C go through the generic tiled kernel. */
+int ogmm_knn_graph(const float* src, int64_t s_sb, int64_t s_sn, int64_t s_sc,
+                   const float* dst, int64_t d_sb, int64_t d_sn, int64_t d_sc,
+                   int64_t B, int64_t N, int64_t M, int64_t C, int64_t k, int normalize,
+                   int64_t* idx_out, float* dist_out, float* edge_out, ogmm_stream_t stream);
+
+/* Edge gather alone, for a caller that already holds idx (lib/utils.py:55-66).
+ *   x (B,C,N) strided view (strides for b, c, n); idx (B,N,k) int64 contiguous, values in [0,N)
+ *   (NOT batch-offset; unlike the reference :57 the index tensor is not modified). */
+int ogmm_edge_gather(const float* x, int64_t sb, int64_t sc, int64_t sn, const int64_t* idx,
+                     int64_t B, int64_t C, int64_t N, int64_t k, float* edge_out, ogmm_stream_t stream);
+
+/* ---- farthest point sampling -----------------------------------------------------------------
+ * Replaces lib/utils.py:170-198 farthest_point_sample.  xyz (B,N,3) strided view.
+ *   start == NULL: is_center=True (start from the point farthest from the centroid);
+ *   otherwise start (B) int64 holds the first index (the reference's torch.randint draw, :190).
+ *   ids_out (B,npoint) int64; pts_out (optional) (B,npoint,3) the gathered points (:111-127). */
+int ogmm_fps(const float* xyz, int64_t sb, int64_t sn, int64_t sc, int64_t B, int64_t N, int64_t npoint,
+             const int64_t* start, int64_t* ids_out, float* pts_out, ogmm_stream_t stream);
+
+/* ---- K2: overlap-guided Sinkhorn k-means (E-step loop + xyz M-step) ---------------------------
+ * Replaces lib/utils.py:269-288 wkeans_plus (FPS init :271-272, marginal :276, and per outer
+ * iteration cdist :280, sinkhorn :74-108, nan_to_num :282, row normalise :287, gmm_params on xyz
+ * :288).  The final feature M-step (:289) is ogmm_gmm_moments_feat.
+ *   xyz (B,N,3) strided view; o_scores (B,N) contiguous.
+ *   gamma_out (B,N,J), pi_out (B,J), mu_out (B,J,3) contiguous.
+ *   The batch-coupled early exit (:99-102) is reproduced exactly: each launch records every
+ *   cloud's per-iteration change, the last CTA to finish evaluates the batch means, and up to
+ *   `iters` follow-up launches (queued on the same stream, immediate exit when not needed) re-run
+ *   from the first outer iteration whose inner count changed.  No host synchronisation.
+ *   workspace: device scratch of at least ogmm_sinkhorn_cluster_workspace(...) bytes; contents
+ *   need not be initialised.  iters_run_out (optional) (iters) int32: inner iterations per outer. */
+int64_t ogmm_sinkhorn_cluster_workspace(int64_t B, int64_t N, int64_t J, int64_t iters, int64_t max_iter);
+int ogmm_sinkhorn_cluster(const float* xyz, int64_t sb, int64_t sn, int64_t sc, const float* o_scores,
+                          int64_t B, int64_t N, int64_t J, int64_t iters, float tau,
+                          float epsilon, float thresh, int64_t max_iter,
+                          float* gamma_out, float* pi_out, float* mu_out, int32_t* iters_run_out,
+                          void* workspace, int64_t workspace_bytes, ogmm_stream_t stream);
+
+/* Stand-alone log-domain Sinkhorn on a given cost matrix (lib/utils.py:74-108).
+ *   cost (B,N,M) contiguous; p (B,N) or NULL (uniform 1/N); q (B,M) or NULL (uniform 1/M).
+ *   gamma_out (B,N,M) = exp(K); loss_out (B) = sum gamma*cost per batch element (the reference
+ *   returns their mean).  Same early-exit protocol and workspace contract as above. */
+int64_t ogmm_sinkhorn_workspace(int64_t B, int64_t N, int64_t M, int64_t max_iter);
+int ogmm_sinkhorn(const float* cost, const float* p, const float* q, int64_t B, int64_t N, int64_t M,
+                  float epsilon, float thresh, int64_t max_iter, float* gamma_out, float* loss_out,
+                  int32_t* iters_run_out, void* workspace, int64_t workspace_bytes, ogmm_stream_t stream);
+
+/* ---- K3: GMM M-step (segmented reductions) -----------------------------------------------------
+ * Replaces lib/utils.py:130-149 gmm_params.
+ *   gamma (B,N,J) strided view (strides b,n,j); pts (B,N,D) strided view (strides b,n,d).
+ *   pi_out (B,J); mu_out (B,J,D); sigma_out (optional) (B,J,D,D) = (sum gamma|x-mu|^2/npi) I.
+ * ogmm_gmm_moments is the small-D kernel (D <= 16, e.g. xyz, with optional sigma);
+ * ogmm_gmm_moments_feat is the streaming kernel for wide features in their native (B,D,N)
+ * layout (pass strides accordingly), reading every feature value from HBM exactly once. */
+int ogmm_gmm_moments(const float* gamma, int64_t g_sb, int64_t g_sn, int64_t g_sj,
+                     const float* pts, int64_t p_sb, int64_t p_sn, int64_t p_sd,
+                     int64_t B, int64_t N, int64_t J, int64_t D,
+                     float* pi_out, float* mu_out, float* sigma_out, ogmm_stream_t stream);
+int ogmm_gmm_moments_feat(const float* gamma, int64_t g_sb, int64_t g_sn, int64_t g_sj,
+                          const float* feats, int64_t f_sb, int64_t f_sn, int64_t f_sd,
+                          int64_t B, int64_t N, int64_t J, int64_t D,
+                          float* pi_out, float* mu_out, ogmm_stream_t stream);
+
+/* DeepGMR closed-form E-step fused with the M-step (baseline/deepgmr.py:71-74 + lib/utils.py:130-148).
+ *   logits (B,J,N) contiguous; pts (B,3,N)-style strided view (strides b,n,d with D == 3).
+ *   gamma_out (optional) (B,J,N) softmax over J; pi_out (B,J); mu_out (B,J,3); sigma_out (B,J,3,3). */
+int ogmm_softmax_moments(const float* logits, const float* pts, int64_t p_sb, int64_t p_sn, int64_t p_sd,
+                         int64_t B, int64_t N, int64_t J,
+                         float* gamma_out, float* pi_out, float* mu_out, float* sigma_out,
+                         ogmm_stream_t stream);
+
+/* ---- K4: weighted Procrustes and the registration heads ------------------------------------------
+ * ogmm_rigid_transform replaces lib/se3.py:256-289 compute_rigid_transformation.
+ *   src, corr (B,3,n) strided views (strides b,c,n); weight (B,1,n) as (ptr, stride b, stride n).
+ *   rot_out (B,3,3), trans_out (B,3) (the reference's (B,3,1) is a view of it). */
+int ogmm_rigid_transform(const float* src, int64_t s_sb, int64_t s_sc, int64_t s_sn,
+                         const float* corr, int64_t c_sb, int64_t c_sc, int64_t c_sn,
+                         const float* weight, int64_t w_sb, int64_t w_sn,
+                         int64_t B, int64_t n, float* rot_out, float* trans_out, ogmm_stream_t stream);
+
+/* ogmm_soft_procrustes replaces models/dgcnn.py:96-115 GMMSVD.forward with is_sk=False (as
+ * constructed at models/gmmreg.py:41): cosine similarity (lib/utils.py:222-226), softmax(sim/T),
+ * soft correspondences, weights, then the Procrustes above -- one kernel, one CTA per pair.
+ *   src_mu (B,Js,3), tgt_mu (B,Jt,3), src_desc (B,Js,D), tgt_desc (B,Jt,D) contiguous.
+ *   rot_out (B,3,3), trans_out (B,3), corr_out (B,3,Js); sim_out (optional) (B,Js,Jt). */
+int ogmm_soft_procrustes(const float* src_mu, const float* tgt_mu, const float* src_desc, const float* tgt_desc,
+                         int64_t B, int64_t Js, int64_t Jt, int64_t D, float temperature,
+                         float* rot_out, float* trans_out, float* corr_out, float* sim_out,
+                         ogmm_stream_t stream);
+
+/* Cosine similarity alone (lib/utils.py:222-226): x (B,N,D), y (B,M,D) contiguous -> (B,N,M). */
+int ogmm_cos_similarity(const float* x, const float* y, int64_t B, int64_t N, int64_t M, int64_t D,
+                        float* sim_out, ogmm_stream_t stream);
+
+/* ogmm_gmm_register replaces baseline/deepgmr.py:17-38 gmm_register.
+ *   pi_s (B,J), mu_s (B,J,3), mu_t (B,J,3), sigma_t (B,J,3,3) contiguous -> transform_out (B,4,4). */
+int ogmm_gmm_register(const float* pi_s, const float* mu_s, const float* mu_t, const float* sigma_t,
+                      int64_t B, int64_t J, float* transform_out, ogmm_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OGMM_B200_H_ */

@@ -1,0 +1,361 @@
+// K1: fused pairwise distance + per-row top-k (+ edge-feature gather) (sm_100a).
+//
+//   knn3_kernel        lib/utils.py:12-44 (+ :47-66 when edge_out is given) for C == 3: one thread per
+//                      query, candidates broadcast from shared memory, FP32 FMA in the reference's
+//                      expanded form  ((-2 s.d) + |s|^2) + |d|^2, clamp 1e-12  -- never the (B,N,M) matrix.
+//   knn_generic_kernel same contract for any C: a 128 x 64 distance tile per CTA step (shared-memory
+//                      tiled FP32 FMA), consumed straight out of shared memory by the same selector.
+//   edge_gather_kernel lib/utils.py:55-66 alone, for a caller that already holds idx.
+//
+// Selection: each query thread keeps its K best (distance, index) pairs sorted in registers.  A
+// candidate that beats the current K-th best is first parked in a small per-thread staging column in
+// shared memory; when any lane of the warp runs low on staging space the whole warp merges its parked
+// candidates into the register lists together (converged, no per-candidate divergence).  Candidates
+// are visited in index order and every comparison is strict, so equal distances resolve to the LOWEST
+// index -- the documented tie-break (torch.topk's own is unspecified).
+#include "common.cuh"
+
+namespace ogmm {
+
+constexpr int kKnnThreads = 256;
+constexpr int kStage = 12;          // staging slots per query thread
+constexpr int kStageTrigger = 8;    // merge when a lane holds more than this many
+
+template <int K>
+struct TopK {
+    float d[K];
+    int i[K];
+    float thr;
+    int cnt;
+    bool live;      // false for padding threads: they take part in the warp votes but never keep anything
+    float* sd;      // staging columns: sd[s * stride + col]
+    int* si;
+    int stride, col;
+
+    __device__ __forceinline__ void init(float* stage_d, int* stage_i, int stride_, int col_, bool live_) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) { d[j] = INFINITY; i[j] = 0; }
+        live = live_;
+        thr = live ? INFINITY : -INFINITY; cnt = 0; sd = stage_d; si = stage_i; stride = stride_; col = col_;
+    }
+    __device__ __forceinline__ void offer(float v, int idx) {
+        if (v < thr) {
+            sd[cnt * stride + col] = v;
+            si[cnt * stride + col] = idx;
+            ++cnt;
+        }
+    }
+    __device__ __forceinline__ void insert(float v, int idx) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const bool lt = v < d[j];
+            const float td = d[j];
+            const int ti = i[j];
+            d[j] = lt ? v : td;
+            i[j] = lt ? idx : ti;
+            v = lt ? td : v;
+            idx = lt ? ti : idx;
+        }
+    }
+    // Warp-converged: every lane of the calling warp must call merge() together.
+    __device__ __forceinline__ void merge() {
+        const int most = __reduce_max_sync(kFull, cnt);
+        for (int s = 0; s < most; ++s) {
+            float v = INFINITY;
+            int idx = 0;
+            if (s < cnt) { v = sd[s * stride + col]; idx = si[s * stride + col]; }
+            if (__any_sync(kFull, v < d[K - 1])) insert(v, idx);
+        }
+        cnt = 0;
+        thr = live ? d[K - 1] : -INFINITY;
+    }
+    __device__ __forceinline__ void maybe_merge() {
+        if (__any_sync(kFull, cnt > kStageTrigger)) merge();
+    }
+};
+
+__device__ __forceinline__ float sq_norm3(float x, float y, float z) {
+    return __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+}
+
+// ---------------------------------------------------------------------------------------------------
+constexpr int kCandTile = 1024;
+
+template <int K>
+__global__ void __launch_bounds__(kKnnThreads)
+knn3_kernel(const float* __restrict__ src, int64_t s_sb, int64_t s_sn, int64_t s_sc,
+            const float* __restrict__ dst, int64_t d_sb, int64_t d_sn, int64_t d_sc,
+            int N, int M, int k, int normalize,
+            int64_t* __restrict__ idx_out, float* __restrict__ dist_out, float* __restrict__ edge_out) {
+    __shared__ float4 s_cand[kCandTile];
+    __shared__ float s_stage_d[kStage * kKnnThreads];
+    __shared__ int s_stage_i[kStage * kKnnThreads];
+
+    const int b = blockIdx.y, tid = threadIdx.x;
+    const int q = blockIdx.x * kKnnThreads + tid;
+    const bool valid = q < N;
+    const float* sb = src + (int64_t)b * s_sb;
+    const float* db = dst + (int64_t)b * d_sb;
+
+    float qx = 0.f, qy = 0.f, qz = 0.f;
+    if (valid) { qx = sb[(int64_t)q * s_sn]; qy = sb[(int64_t)q * s_sn + s_sc]; qz = sb[(int64_t)q * s_sn + 2 * s_sc]; }
+    const float qs = normalize ? 2.0f : sq_norm3(qx, qy, qz);
+
+    TopK<K> top;
+    top.init(s_stage_d, s_stage_i, kKnnThreads, tid, valid);
+
+    for (int m0 = 0; m0 < M; m0 += kCandTile) {
+        const int len = min(kCandTile, M - m0);
+        const int len4 = (len + 3) & ~3;
+        __syncthreads();
+        for (int m = tid; m < len4; m += kKnnThreads) {
+            float4 c = make_float4(0.f, 0.f, 0.f, INFINITY);
+            if (m < len) {
+                const float* p = db + (int64_t)(m0 + m) * d_sn;
+                const float x = p[0], y = p[d_sc], z = p[2 * d_sc];
+                c = make_float4(-2.f * x, -2.f * y, -2.f * z, normalize ? 0.f : sq_norm3(x, y, z));
+            }
+            s_cand[m] = c;
+        }
+        __syncthreads();
+        for (int m = 0; m < len4; m += 4) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float4 c = s_cand[m + u];
+                // (-2 s.d) accumulated like a K=3 GEMM, then + |s|^2, then + |d|^2 (lib/utils.py:28-32)
+                float v = __fmul_rn(qx, c.x);
+                v = fmaf(qy, c.y, v);
+                v = fmaf(qz, c.z, v);
+                v = __fadd_rn(__fadd_rn(v, qs), c.w);
+                if (!normalize) v = fmaxf(v, 1e-12f);
+                top.offer(v, m0 + m + u);
+            }
+            top.maybe_merge();
+        }
+    }
+    top.merge();
+
+    if (!valid) return;
+    int64_t* io = idx_out + ((int64_t)b * N + q) * k;
+    float* dout = dist_out ? dist_out + ((int64_t)b * N + q) * k : nullptr;
+    float* eo = edge_out ? edge_out + ((int64_t)b * N + q) * (int64_t)k * 6 : nullptr;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        if (j < k) {
+            io[j] = top.i[j];
+            if (dout) dout[j] = top.d[j];
+            if (eo) {
+                const float* p = sb + (int64_t)top.i[j] * s_sn;       // self graph: neighbours live in src
+                eo[6 * j + 0] = p[0] - qx; eo[6 * j + 1] = p[s_sc] - qy; eo[6 * j + 2] = p[2 * s_sc] - qz;
+                eo[6 * j + 3] = qx; eo[6 * j + 4] = qy; eo[6 * j + 5] = qz;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// generic C: CTA tile = 128 queries x 64 candidates, 256 threads, 8 x 4 register tile per thread.
+constexpr int kGQ = 128, kGC = 64, kGK = 16;
+constexpr size_t kGenericSmem = sizeof(float) * (kGK * (kGQ + 4) + kGK * (kGC + 4) + kGQ * (kGC + 1) + kGQ + kGC + 2 * kStage * kGQ);
+
+template <int K>
+__global__ void __launch_bounds__(kKnnThreads)
+knn_generic_kernel(const float* __restrict__ src, int64_t s_sb, int64_t s_sn, int64_t s_sc,
+                   const float* __restrict__ dst, int64_t d_sb, int64_t d_sn, int64_t d_sc,
+                   int N, int M, int C, int k, int normalize,
+                   int64_t* __restrict__ idx_out, float* __restrict__ dist_out, float* __restrict__ edge_out) {
+    extern __shared__ __align__(16) float g_sm[];
+    float (*s_a)[kGQ + 4] = reinterpret_cast<float (*)[kGQ + 4]>(g_sm);                       // query chunk, transposed
+    float (*s_b)[kGC + 4] = reinterpret_cast<float (*)[kGC + 4]>(g_sm + kGK * (kGQ + 4));     // candidate chunk, transposed
+    float (*s_dist)[kGC + 1] = reinterpret_cast<float (*)[kGC + 1]>(g_sm + kGK * (kGQ + 4) + kGK * (kGC + 4));
+    float* s_qn = g_sm + kGK * (kGQ + 4) + kGK * (kGC + 4) + kGQ * (kGC + 1);
+    float* s_cn = s_qn + kGQ;
+    float* s_stage_d = s_cn + kGC;
+    int* s_stage_i = reinterpret_cast<int*>(s_stage_d + kStage * kGQ);
+
+    const int b = blockIdx.y, tid = threadIdx.x;
+    const int q0 = blockIdx.x * kGQ;
+    const float* sb = src + (int64_t)b * s_sb;
+    const float* db = dst + (int64_t)b * d_sb;
+    const int tq = (tid >> 4) * 8;      // 16 thread rows x 8 queries
+    const int tc = (tid & 15) * 4;      // 16 thread cols x 4 candidates
+
+    // |q|^2 per query (sequential over c, products rounded separately like sum(src ** 2, -1))
+    if (tid < kGQ) {
+        float acc = 0.f;
+        if (q0 + tid < N && !normalize)
+            for (int c = 0; c < C; ++c) { const float v = sb[(int64_t)(q0 + tid) * s_sn + (int64_t)c * s_sc]; acc = __fadd_rn(acc, __fmul_rn(v, v)); }
+        s_qn[tid] = normalize ? 2.0f : acc;
+    }
+
+    TopK<K> top;
+    const bool selector = tid < kGQ;
+    const bool valid = selector && (q0 + tid < N);
+    top.init(s_stage_d, s_stage_i, kGQ, tid & (kGQ - 1), valid);
+
+    for (int m0 = 0; m0 < M; m0 += kGC) {
+        float acc[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        __syncthreads();
+        if (tid < kGC) {
+            float a = 0.f;
+            if (m0 + tid < M && !normalize)
+                for (int c = 0; c < C; ++c) { const float v = db[(int64_t)(m0 + tid) * d_sn + (int64_t)c * d_sc]; a = __fadd_rn(a, __fmul_rn(v, v)); }
+            s_cn[tid] = (m0 + tid < M) ? (normalize ? 0.f : a) : INFINITY;
+        }
+        for (int c0 = 0; c0 < C; c0 += kGK) {
+            __syncthreads();
+            for (int e = tid; e < kGQ * kGK; e += kKnnThreads) {
+                int r, c;
+                if (s_sc == 1) { r = e / kGK; c = e - r * kGK; } else { c = e / kGQ; r = e - c * kGQ; }
+                float v = 0.f;
+                if (q0 + r < N && c0 + c < C) v = sb[(int64_t)(q0 + r) * s_sn + (int64_t)(c0 + c) * s_sc];
+                s_a[c][r] = v;
+            }
+            for (int e = tid; e < kGC * kGK; e += kKnnThreads) {
+                int r, c;
+                if (d_sc == 1) { r = e / kGK; c = e - r * kGK; } else { c = e / kGC; r = e - c * kGC; }
+                float v = 0.f;
+                if (m0 + r < M && c0 + c < C) v = db[(int64_t)(m0 + r) * d_sn + (int64_t)(c0 + c) * d_sc];
+                s_b[c][r] = -2.f * v;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int c = 0; c < kGK; ++c) {
+                float av[8], bv[4];
+#pragma unroll
+                for (int i = 0; i < 8; i += 4) *reinterpret_cast<float4*>(av + i) = *reinterpret_cast<const float4*>(&s_a[c][tq + i]);
+                *reinterpret_cast<float4*>(bv) = *reinterpret_cast<const float4*>(&s_b[c][tc]);
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float v = __fadd_rn(__fadd_rn(acc[i][j], s_qn[tq + i]), s_cn[tc + j]);
+                if (!normalize) v = fmaxf(v, 1e-12f);
+                s_dist[tq + i][tc + j] = v;
+            }
+        __syncthreads();
+        if (tid < kGQ) {                      // warps 0..3 are the selectors (warp-uniform branch)
+            for (int c = 0; c < kGC; c += 4) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) top.offer(s_dist[tid][c + u], m0 + c + u);
+                top.maybe_merge();
+            }
+        }
+    }
+    if (tid < kGQ) top.merge();
+    if (!valid) return;
+    const int q = q0 + tid;
+    int64_t* io = idx_out + ((int64_t)b * N + q) * k;
+    float* dout = dist_out ? dist_out + ((int64_t)b * N + q) * k : nullptr;
+#pragma unroll
+    for (int j = 0; j < K; ++j)
+        if (j < k) { io[j] = top.i[j]; if (dout) dout[j] = top.d[j]; }
+    if (edge_out) {
+        float* eo = edge_out + ((int64_t)b * N + q) * (int64_t)k * 2 * C;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            if (j < k) {
+                for (int c = 0; c < C; ++c) {
+                    const float ctr = sb[(int64_t)q * s_sn + (int64_t)c * s_sc];
+                    eo[(int64_t)j * 2 * C + c] = sb[(int64_t)top.i[j] * s_sn + (int64_t)c * s_sc] - ctr;
+                    eo[(int64_t)j * 2 * C + C + c] = ctr;
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// edge gather: out[b][n][kk][0:C] = x[:, idx] - x[:, n]; out[..][C:2C] = x[:, n].  One thread per
+// (b, n, kk, c) element pair, consecutive threads write consecutive floats.
+__global__ void __launch_bounds__(256)
+edge_gather_kernel(const float* __restrict__ x, int64_t sb, int64_t sc, int64_t sn, const int64_t* __restrict__ idx,
+                   int64_t total, int C, int N, int k, float* __restrict__ out) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const int c2 = (int)(e % (2 * C));
+    const int64_t row = e / (2 * C);          // (b, n, kk)
+    const int64_t bn = row / k;
+    const int n = (int)(bn % N);
+    const int64_t b = bn / N;
+    const float* xb = x + b * sb;
+    const int c = c2 < C ? c2 : c2 - C;
+    const float ctr = xb[(int64_t)c * sc + (int64_t)n * sn];
+    float v = ctr;
+    if (c2 < C) {
+        int64_t j = idx[row];
+        j = j < 0 ? 0 : (j >= N ? N - 1 : j);
+        v = xb[(int64_t)c * sc + j * sn] - ctr;
+    }
+    out[e] = v;
+}
+
+}  // namespace ogmm
+
+using namespace ogmm;
+
+extern "C" __attribute__((visibility("default"))) int ogmm_knn_graph(const float* src, int64_t s_sb, int64_t s_sn, int64_t s_sc,
+                              const float* dst, int64_t d_sb, int64_t d_sn, int64_t d_sc,
+                              int64_t B, int64_t N, int64_t M, int64_t C, int64_t k, int normalize,
+                              int64_t* idx_out, float* dist_out, float* edge_out, ogmm_stream_t stream) {
+    OGMM_REQUIRE(B >= 0 && N >= 1 && M >= 1 && C >= 1 && k >= 1 && N < (1ll << 31) && M < (1ll << 31) && B < 65536,
+                 OGMM_EINVAL, "ogmm_knn_graph: bad sizes B=%lld N=%lld M=%lld C=%lld k=%lld", (long long)B,
+                 (long long)N, (long long)M, (long long)C, (long long)k);
+    OGMM_REQUIRE(k <= M, OGMM_EINVAL, "ogmm_knn_graph: k=%lld exceeds the number of candidates M=%lld", (long long)k, (long long)M);
+    OGMM_REQUIRE(k <= 64, OGMM_EUNSUPPORTED, "ogmm_knn_graph: k=%lld > 64", (long long)k);
+    if (B == 0) return OGMM_OK;
+    OGMM_REQUIRE(src && dst && idx_out, OGMM_EINVAL, "ogmm_knn_graph: null pointer");
+    OGMM_REQUIRE(edge_out == nullptr || (N == M), OGMM_EINVAL, "ogmm_knn_graph: edge_out needs a self graph (N == M)");
+    cudaStream_t s = as_stream(stream);
+    const bool three = (C == 3);
+    dim3 grid((unsigned)((N + (three ? kKnnThreads : kGQ) - 1) / (three ? kKnnThreads : kGQ)), (unsigned)B);
+#define LAUNCH(KK)                                                                                                   \
+    do {                                                                                                             \
+        if (three)                                                                                                   \
+            knn3_kernel<KK><<<grid, kKnnThreads, 0, s>>>(src, s_sb, s_sn, s_sc, dst, d_sb, d_sn, d_sc, (int)N,      \
+                                                         (int)M, (int)k, normalize, idx_out, dist_out, edge_out);   \
+        else {                                                                                                       \
+            int st = cuda_status(cudaFuncSetAttribute(knn_generic_kernel<KK>,                                        \
+                                                      cudaFuncAttributeMaxDynamicSharedMemorySize,                   \
+                                                      (int)kGenericSmem), "cudaFuncSetAttribute(knn_generic)");     \
+            if (st != OGMM_OK) return st;                                                                            \
+            knn_generic_kernel<KK><<<grid, kKnnThreads, kGenericSmem, s>>>(src, s_sb, s_sn, s_sc, dst, d_sb, d_sn,  \
+                                                                           d_sc, (int)N, (int)M, (int)C, (int)k,    \
+                                                                           normalize, idx_out, dist_out, edge_out); \
+        }                                                                                                            \
+    } while (0)
+    if (k <= 4) LAUNCH(4);
+    else if (k <= 8) LAUNCH(8);
+    else if (k <= 16) LAUNCH(16);
+    else if (k <= 20) LAUNCH(20);
+    else if (k <= 32) LAUNCH(32);
+    else LAUNCH(64);
+#undef LAUNCH
+    OGMM_LAUNCH_CHECK("knn kernel");
+    return OGMM_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int ogmm_edge_gather(const float* x, int64_t sb, int64_t sc, int64_t sn, const int64_t* idx,
+                                int64_t B, int64_t C, int64_t N, int64_t k, float* edge_out, ogmm_stream_t stream) {
+    OGMM_REQUIRE(B >= 0 && C >= 1 && N >= 1 && k >= 1 && N < (1ll << 31) && C < (1ll << 20) && k < (1ll << 20),
+                 OGMM_EINVAL, "ogmm_edge_gather: bad sizes");
+    if (B == 0) return OGMM_OK;
+    OGMM_REQUIRE(x && idx && edge_out, OGMM_EINVAL, "ogmm_edge_gather: null pointer");
+    const int64_t total = B * N * k * 2 * C;
+    const int64_t blocks = (total + 255) / 256;
+    OGMM_REQUIRE(blocks < (1ll << 31), OGMM_EUNSUPPORTED, "ogmm_edge_gather: output too large");
+    edge_gather_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(x, sb, sc, sn, idx, total, (int)C, (int)N,
+                                                                        (int)k, edge_out);
+    OGMM_LAUNCH_CHECK("edge_gather_kernel");
+    return OGMM_OK;
+}

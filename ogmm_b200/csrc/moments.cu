@@ -1,0 +1,422 @@
+// K3: GMM M-step as segmented reductions (sm_100a).
+//
+//   gmm_moments_small_kernel   lib/utils.py:130-149  pi, mu (+ isotropic sigma) for D <= 4 (xyz)
+//   gmm_moments_feat_kernel    lib/utils.py:130-140  mu for wide features, streamed once from HBM in
+//                              their native (B,D,N) layout (models/gmmreg.py:26-27 passes a view)
+//   softmax_moments_kernel     baseline/deepgmr.py:71-74 softmax over J fused with the M-step + sigma
+//
+// Quirks kept from the reference: npi = pi*N + 1e-5 (:138); sigma = sum_n gamma |x-mu|^2 / npi, NOT
+// divided by D (:146-147); pi is the plain mean of whatever gamma holds (rows need not sum to 1).
+#include "common.cuh"
+
+namespace ogmm {
+
+// =====================================================================================================
+// small-D kernel: one CTA per cloud, lanes over j, warps (and lane groups when J | 32) over n.
+// =====================================================================================================
+constexpr int kSmallThreads = 256;
+constexpr int kSmallD = 4;          // D <= 4
+constexpr int kSmallSlots = 4;      // J <= 128 per pass
+
+template <bool kSigmaPass>
+__device__ __forceinline__ void small_accumulate(const float* __restrict__ g, int64_t g_sn, int64_t g_sj,
+                                                 const float* __restrict__ x, int64_t p_sn, int64_t p_sd, int N,
+                                                 int J, int D, int j_base, const float* __restrict__ s_mu,
+                                                 float (&acc)[kSmallSlots][kSmallD + 1]) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = kSmallThreads / 32;
+    // lane layout: when J <= 32 divides 32, 32/J rows share a warp; otherwise one row per warp step
+    const int rows_per_warp = (J <= 32 && (32 % J) == 0) ? 32 / J : 1;
+    const int jl = rows_per_warp > 1 ? lane % J : lane;
+    const int rsub = rows_per_warp > 1 ? lane / J : 0;
+    for (int n = warp * rows_per_warp + rsub; n < N; n += NW * rows_per_warp) {
+        float xv[kSmallD];
+#pragma unroll
+        for (int d = 0; d < kSmallD; ++d) xv[d] = d < D ? x[(int64_t)n * p_sn + d * p_sd] : 0.f;
+#pragma unroll
+        for (int s = 0; s < kSmallSlots; ++s) {
+            const int j = j_base + jl + 32 * s;
+            if ((rows_per_warp > 1 && s > 0) || j >= J) continue;
+            const float gv = g[(int64_t)n * g_sn + (int64_t)j * g_sj];
+            if constexpr (!kSigmaPass) {
+                acc[s][0] += gv;
+#pragma unroll
+                for (int d = 0; d < kSmallD; ++d) acc[s][d + 1] = fmaf(gv, xv[d], acc[s][d + 1]);
+            } else {
+                float sq = 0.f;
+#pragma unroll
+                for (int d = 0; d < kSmallD; ++d) {
+                    const float df = d < D ? xv[d] - s_mu[j * kSmallD + d] : 0.f;
+                    sq = fmaf(df, df, sq);
+                }
+                acc[s][0] = fmaf(sq, gv, acc[s][0]);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kSmallThreads)
+gmm_moments_small_kernel(const float* __restrict__ gamma, int64_t g_sb, int64_t g_sn, int64_t g_sj,
+                         const float* __restrict__ pts, int64_t p_sb, int64_t p_sn, int64_t p_sd,
+                         int N, int J, int D, float* __restrict__ pi_out, float* __restrict__ mu_out,
+                         float* __restrict__ sigma_out) {
+    extern __shared__ __align__(16) float sm[];
+    constexpr int NW = kSmallThreads / 32;
+    // s_part [NW][128][5] | s_mu [J][4] | s_npi [J]
+    float* s_part = sm;
+    float* s_mu = s_part + NW * 128 * (kSmallD + 1);
+    float* s_npi = s_mu + (size_t)J * kSmallD;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* g = gamma + (int64_t)b * g_sb;
+    const float* x = pts + (int64_t)b * p_sb;
+    const int rows_per_warp = (J <= 32 && (32 % J) == 0) ? 32 / J : 1;
+
+    for (int pass = 0; pass < (sigma_out ? 2 : 1); ++pass) {
+        for (int j_base = 0; j_base < J; j_base += 128) {
+            float acc[kSmallSlots][kSmallD + 1];
+#pragma unroll
+            for (int s = 0; s < kSmallSlots; ++s)
+#pragma unroll
+                for (int d = 0; d <= kSmallD; ++d) acc[s][d] = 0.f;
+            if (pass == 0) small_accumulate<false>(g, g_sn, g_sj, x, p_sn, p_sd, N, J, D, j_base, s_mu, acc);
+            else small_accumulate<true>(g, g_sn, g_sj, x, p_sn, p_sd, N, J, D, j_base, s_mu, acc);
+            // combine lane groups that share a column
+            if (rows_per_warp > 1) {
+                for (int off = 16; off >= J; off >>= 1)
+#pragma unroll
+                    for (int d = 0; d <= kSmallD; ++d) acc[0][d] += __shfl_xor_sync(kFull, acc[0][d], off);
+            }
+            __syncthreads();
+#pragma unroll
+            for (int s = 0; s < kSmallSlots; ++s) {
+                const int jj = (rows_per_warp > 1 ? lane % J : lane) + 32 * s;
+                if (rows_per_warp > 1 && (s > 0 || lane >= J)) continue;
+                if (j_base + jj >= J) continue;
+#pragma unroll
+                for (int d = 0; d <= kSmallD; ++d) s_part[(warp * 128 + jj) * (kSmallD + 1) + d] = acc[s][d];
+            }
+            __syncthreads();
+            for (int jj = tid; jj < 128 && j_base + jj < J; jj += kSmallThreads) {
+                const int j = j_base + jj;
+                float t[kSmallD + 1];
+#pragma unroll
+                for (int d = 0; d <= kSmallD; ++d) t[d] = 0.f;
+                for (int w = 0; w < NW; ++w)
+#pragma unroll
+                    for (int d = 0; d <= kSmallD; ++d) t[d] += s_part[(w * 128 + jj) * (kSmallD + 1) + d];
+                if (pass == 0) {
+                    const float pi = __fdiv_rn(t[0], (float)N);
+                    const float npi = __fadd_rn(__fmul_rn(pi, (float)N), 1e-5f);
+                    pi_out[(int64_t)b * J + j] = pi;
+                    s_npi[j] = npi;
+#pragma unroll
+                    for (int d = 0; d < kSmallD; ++d) {
+                        const float m = __fdiv_rn(t[d + 1], npi);
+                        s_mu[j * kSmallD + d] = m;
+                        if (d < D) mu_out[((int64_t)b * J + j) * D + d] = m;
+                    }
+                } else {
+                    const float sg = __fdiv_rn(t[0], s_npi[j]);
+                    float* so = sigma_out + ((int64_t)b * J + j) * D * D;
+                    for (int r = 0; r < D; ++r)
+                        for (int c = 0; c < D; ++c) so[r * D + c] = r == c ? sg : 0.f;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// =====================================================================================================
+// wide-feature kernel.  out[j][d] = sum_n gamma[n][j] * f[n][d] / npi[j].
+// CTA = (d tile of TD = 8*DT rows, one cloud).  Each warp owns DT feature rows, each lane an n
+// residue; a thread keeps DT x JP accumulators in registers.  The feature tile [TD][TN] and the gamma
+// tile [TN][JP] are staged through shared memory with coalesced loads; every feature value is read
+// from global memory exactly once, gamma is re-read per d tile (from L2: it was just written).
+// =====================================================================================================
+constexpr int kFeatThreads = 256;
+constexpr int kTN = 128;
+constexpr int kFPad = kTN + 4;
+
+template <int JP, int DT>
+__global__ void __launch_bounds__(kFeatThreads)
+gmm_moments_feat_kernel(const float* __restrict__ gamma, int64_t g_sb, int64_t g_sn, int64_t g_sj,
+                        const float* __restrict__ feats, int64_t f_sb, int64_t f_sn, int64_t f_sd,
+                        int N, int J, int D, float* __restrict__ pi_out, float* __restrict__ mu_out) {
+    constexpr int TD = 8 * DT;
+    constexpr int GP = JP + 4;                      // padded gamma row: conflict-free 128-bit reads
+    extern __shared__ __align__(16) float sm[];
+    float* s_f = sm;                                // [TD][kFPad]
+    float* s_g = s_f + TD * kFPad;                  // [kTN][GP]
+    float* s_red = s_g + kTN * GP;                  // [8][JP] column sums of gamma per warp
+    const int b = blockIdx.y, d0 = blockIdx.x * TD;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* g = gamma + (int64_t)b * g_sb;
+    const float* f = feats + (int64_t)b * f_sb;
+
+    float acc[DT][JP];
+#pragma unroll
+    for (int i = 0; i < DT; ++i)
+#pragma unroll
+        for (int j = 0; j < JP; ++j) acc[i][j] = 0.f;
+    float gsum = 0.f;                               // partial sum of gamma column tid % JP
+
+    const bool f_vec = (f_sn == 1) && ((f_sd & 3) == 0) && ((f_sb & 3) == 0) && ((reinterpret_cast<uintptr_t>(feats) & 15) == 0);
+    const bool g_vec = (g_sj == 1) && (g_sn == J) && ((J & 3) == 0) && ((g_sb & 3) == 0) && ((reinterpret_cast<uintptr_t>(gamma) & 15) == 0);
+
+    for (int n0 = 0; n0 < N; n0 += kTN) {
+        const int tn = min(kTN, N - n0);
+        __syncthreads();
+        // ---- feature tile
+        if (f_vec && tn == kTN) {
+            for (int e = tid; e < TD * (kTN / 4); e += kFeatThreads) {
+                const int r = e / (kTN / 4), c4 = e - r * (kTN / 4);
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (d0 + r < D) v = ldg_stream4(f + (int64_t)(d0 + r) * f_sd + n0 + 4 * c4);
+                *reinterpret_cast<float4*>(s_f + r * kFPad + 4 * c4) = v;
+            }
+        } else if (f_sd == 1) {
+            // (B,N,D) row-major features: sweep d fastest for coalescing
+            for (int e = tid; e < TD * kTN; e += kFeatThreads) {
+                const int c = e / TD, r = e - c * TD;
+                float v = 0.f;
+                if (d0 + r < D && c < tn) v = ldg_stream(f + (int64_t)(n0 + c) * f_sn + (d0 + r));
+                s_f[r * kFPad + c] = v;
+            }
+        } else {
+            for (int e = tid; e < TD * kTN; e += kFeatThreads) {
+                const int r = e / kTN, c = e - r * kTN;
+                float v = 0.f;
+                if (d0 + r < D && c < tn) v = ldg_stream(f + (int64_t)(n0 + c) * f_sn + (int64_t)(d0 + r) * f_sd);
+                s_f[r * kFPad + c] = v;
+            }
+        }
+        // ---- gamma tile
+        if (g_vec && tn == kTN && JP == J) {
+            const float4* src = reinterpret_cast<const float4*>(g + (int64_t)n0 * J);
+            for (int e = tid; e < kTN * (JP / 4); e += kFeatThreads) {
+                const int r = e / (JP / 4), c4 = e - r * (JP / 4);
+                *reinterpret_cast<float4*>(s_g + r * GP + 4 * c4) = src[e];
+            }
+        } else {
+            for (int e = tid; e < kTN * JP; e += kFeatThreads) {
+                const int r = e / JP, c = e - r * JP;
+                float v = 0.f;
+                if (r < tn && c < J) v = g[(int64_t)(n0 + r) * g_sn + (int64_t)c * g_sj];
+                s_g[r * GP + c] = v;
+            }
+        }
+        __syncthreads();
+        // ---- gamma column sums (only the d0 == 0 tile publishes pi, but npi is needed by every tile)
+        for (int r = tid / JP; r < kTN; r += kFeatThreads / JP) gsum += s_g[r * GP + (tid % JP)];
+        // ---- accumulate
+#pragma unroll
+        for (int t = 0; t < kTN / 32; ++t) {
+            const int n = lane + 32 * t;
+            float fv[DT];
+#pragma unroll
+            for (int i = 0; i < DT; ++i) fv[i] = s_f[(warp * DT + i) * kFPad + n];
+            const float4* grow = reinterpret_cast<const float4*>(s_g + n * GP);
+#pragma unroll
+            for (int j4 = 0; j4 < JP / 4; ++j4) {
+                const float4 gv = grow[j4];
+#pragma unroll
+                for (int i = 0; i < DT; ++i) {
+                    acc[i][4 * j4 + 0] = fmaf(gv.x, fv[i], acc[i][4 * j4 + 0]);
+                    acc[i][4 * j4 + 1] = fmaf(gv.y, fv[i], acc[i][4 * j4 + 1]);
+                    acc[i][4 * j4 + 2] = fmaf(gv.z, fv[i], acc[i][4 * j4 + 2]);
+                    acc[i][4 * j4 + 3] = fmaf(gv.w, fv[i], acc[i][4 * j4 + 3]);
+                }
+            }
+        }
+    }
+    // ---- reduce gamma column sums: threads with equal tid % JP hold partials of one column
+    __syncthreads();
+    float* s_col = s_g;                              // reuse: [kFeatThreads]
+    s_col[tid] = gsum;
+    __syncthreads();
+    if (tid < JP) {
+        float t = 0.f;
+        for (int r = tid; r < kFeatThreads; r += JP) t += s_col[r];
+        const float pi = __fdiv_rn(t, (float)N);
+        s_red[tid] = __fadd_rn(__fmul_rn(pi, (float)N), 1e-5f);
+        if (blockIdx.x == 0 && tid < J && pi_out) pi_out[(int64_t)b * J + tid] = pi;
+    }
+    __syncthreads();
+    // ---- reduce accumulators over the 32 n residues of each warp (16-column butterflies)
+#pragma unroll
+    for (int i = 0; i < DT; ++i) {
+        const int d = d0 + warp * DT + i;
+#pragma unroll
+        for (int jc = 0; jc < JP / kJC; ++jc) {
+            float part[kJC];
+#pragma unroll
+            for (int jj = 0; jj < kJC; ++jj) part[jj] = acc[i][jc * kJC + jj];
+            const float t = butterfly16(part, lane);
+            const int j = jc * kJC + ((lane >> 1) & 15);
+            if ((lane & 1) == 0 && d < D && j < J) mu_out[((int64_t)b * J + j) * D + d] = __fdiv_rn(t, s_red[j]);
+        }
+    }
+}
+
+// =====================================================================================================
+// DeepGMR: gamma = softmax_j(logits[b,:,n]); pi, mu, sigma as above.  One CTA per cloud.  Thread per
+// point; the softmax row is recomputed in the sigma pass rather than stored (logits stay L2-resident).
+// =====================================================================================================
+constexpr int kSoftThreads = 256;
+
+__global__ void __launch_bounds__(kSoftThreads)
+softmax_moments_kernel(const float* __restrict__ logits, const float* __restrict__ pts, int64_t p_sb, int64_t p_sn,
+                       int64_t p_sd, int N, int J, float* __restrict__ gamma_out, float* __restrict__ pi_out,
+                       float* __restrict__ mu_out, float* __restrict__ sigma_out) {
+    extern __shared__ __align__(16) float sm[];
+    constexpr int NW = kSoftThreads / 32;
+    float* s_part = sm;                              // [NW][J][4]
+    float* s_mu = s_part + (size_t)NW * J * 4;       // [J][4]: mu xyz, npi
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* lg = logits + (int64_t)b * J * N;
+    const float* x = pts + (int64_t)b * p_sb;
+
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int e = tid; e < NW * J * 4; e += kSoftThreads) s_part[e] = 0.f;
+        __syncthreads();
+        for (int n0 = 0; n0 < N; n0 += kSoftThreads) {
+            const int n = n0 + tid;
+            const bool ok = n < N;
+            float mx = -INFINITY, den = 0.f, px = 0.f, py = 0.f, pz = 0.f;
+            if (ok) {
+                px = x[(int64_t)n * p_sn]; py = x[(int64_t)n * p_sn + p_sd]; pz = x[(int64_t)n * p_sn + 2 * p_sd];
+                for (int j = 0; j < J; ++j) mx = fmaxf(mx, lg[(int64_t)j * N + n]);
+                for (int j = 0; j < J; ++j) den += expf(lg[(int64_t)j * N + n] - mx);
+            }
+            for (int j = 0; j < J; ++j) {
+                float gv = 0.f;
+                if (ok) {
+                    gv = __fdiv_rn(expf(lg[(int64_t)j * N + n] - mx), den);
+                    if (pass == 0 && gamma_out) gamma_out[((int64_t)b * J + j) * N + n] = gv;
+                }
+                float a0, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                if (pass == 0) { a0 = gv; a1 = gv * px; a2 = gv * py; a3 = gv * pz; }
+                else {
+                    const float dx = px - s_mu[4 * j], dy = py - s_mu[4 * j + 1], dz = pz - s_mu[4 * j + 2];
+                    a0 = fmaf(dz, dz, fmaf(dy, dy, dx * dx)) * gv;
+                }
+                a0 = warp_sum(a0);
+                if (pass == 0) { a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3); }
+                if (lane == 0) {
+                    float* p = s_part + ((size_t)warp * J + j) * 4;
+                    p[0] += a0; p[1] += a1; p[2] += a2; p[3] += a3;
+                }
+            }
+        }
+        __syncthreads();
+        for (int j = tid; j < J; j += kSoftThreads) {
+            float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+            for (int w = 0; w < NW; ++w) {
+                const float* p = s_part + ((size_t)w * J + j) * 4;
+                t0 += p[0]; t1 += p[1]; t2 += p[2]; t3 += p[3];
+            }
+            if (pass == 0) {
+                const float pi = __fdiv_rn(t0, (float)N);
+                const float npi = __fadd_rn(__fmul_rn(pi, (float)N), 1e-5f);
+                pi_out[(int64_t)b * J + j] = pi;
+                const float m0 = __fdiv_rn(t1, npi), m1 = __fdiv_rn(t2, npi), m2 = __fdiv_rn(t3, npi);
+                s_mu[4 * j] = m0; s_mu[4 * j + 1] = m1; s_mu[4 * j + 2] = m2; s_mu[4 * j + 3] = npi;
+                float* m = mu_out + ((int64_t)b * J + j) * 3;
+                m[0] = m0; m[1] = m1; m[2] = m2;
+            } else if (sigma_out) {
+                const float sg = __fdiv_rn(t0, s_mu[4 * j + 3]);
+                float* so = sigma_out + ((int64_t)b * J + j) * 9;
+                so[0] = sg; so[1] = 0.f; so[2] = 0.f; so[3] = 0.f; so[4] = sg; so[5] = 0.f; so[6] = 0.f; so[7] = 0.f; so[8] = sg;
+            }
+        }
+        __syncthreads();
+        if (!sigma_out) break;
+    }
+}
+
+}  // namespace ogmm
+
+using namespace ogmm;
+
+extern "C" __attribute__((visibility("default"))) int ogmm_gmm_moments_feat(const float* gamma, int64_t g_sb, int64_t g_sn, int64_t g_sj,
+                                     const float* feats, int64_t f_sb, int64_t f_sn, int64_t f_sd,
+                                     int64_t B, int64_t N, int64_t J, int64_t D,
+                                     float* pi_out, float* mu_out, ogmm_stream_t stream) {
+    OGMM_REQUIRE(B >= 0 && N >= 1 && J >= 1 && D >= 1 && B < 65536 && N < (1ll << 31), OGMM_EINVAL,
+                 "ogmm_gmm_moments_feat: bad sizes B=%lld N=%lld J=%lld D=%lld", (long long)B, (long long)N,
+                 (long long)J, (long long)D);
+    OGMM_REQUIRE(J <= 128, OGMM_EUNSUPPORTED, "ogmm_gmm_moments_feat: J=%lld > 128", (long long)J);
+    if (B == 0) return OGMM_OK;
+    OGMM_REQUIRE(gamma && feats && mu_out, OGMM_EINVAL, "ogmm_gmm_moments_feat: null pointer");
+    cudaStream_t s = as_stream(stream);
+#define LAUNCH(JP, DT)                                                                                              \
+    do {                                                                                                            \
+        constexpr int TD = 8 * DT;                                                                                  \
+        const size_t smem = sizeof(float) * ((size_t)TD * kFPad + (size_t)kTN * (JP + 4) + JP + 32);                \
+        if (smem > 48 * 1024) {                                                                                     \
+            int st = cuda_status(cudaFuncSetAttribute(gmm_moments_feat_kernel<JP, DT>,                              \
+                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),      \
+                                 "cudaFuncSetAttribute(gmm_moments_feat_kernel)");                                  \
+            if (st != OGMM_OK) return st;                                                                           \
+        }                                                                                                           \
+        dim3 grid((unsigned)((D + TD - 1) / TD), (unsigned)B);                                                      \
+        gmm_moments_feat_kernel<JP, DT><<<grid, kFeatThreads, smem, s>>>(gamma, g_sb, g_sn, g_sj, feats, f_sb,      \
+                                                                         f_sn, f_sd, (int)N, (int)J, (int)D,        \
+                                                                         pi_out, mu_out);                           \
+    } while (0)
+    if (J <= 16) LAUNCH(16, 4);
+    else if (J <= 32) LAUNCH(32, 2);
+    else if (J <= 64) LAUNCH(64, 1);
+    else LAUNCH(128, 1);
+#undef LAUNCH
+    OGMM_LAUNCH_CHECK("gmm_moments_feat_kernel");
+    return OGMM_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int ogmm_gmm_moments(const float* gamma, int64_t g_sb, int64_t g_sn, int64_t g_sj,
+                                const float* pts, int64_t p_sb, int64_t p_sn, int64_t p_sd,
+                                int64_t B, int64_t N, int64_t J, int64_t D,
+                                float* pi_out, float* mu_out, float* sigma_out, ogmm_stream_t stream) {
+    OGMM_REQUIRE(B >= 0 && N >= 1 && J >= 1 && D >= 1 && B < (1ll << 31) && N < (1ll << 31), OGMM_EINVAL,
+                 "ogmm_gmm_moments: bad sizes B=%lld N=%lld J=%lld D=%lld", (long long)B, (long long)N, (long long)J,
+                 (long long)D);
+    if (B == 0) return OGMM_OK;
+    OGMM_REQUIRE(gamma && pts && pi_out && mu_out, OGMM_EINVAL, "ogmm_gmm_moments: null pointer");
+    if (D > kSmallD) {
+        OGMM_REQUIRE(sigma_out == nullptr, OGMM_EUNSUPPORTED, "ogmm_gmm_moments: sigma is built for D <= %d, got D=%lld",
+                     kSmallD, (long long)D);
+        return ogmm_gmm_moments_feat(gamma, g_sb, g_sn, g_sj, pts, p_sb, p_sn, p_sd, B, N, J, D, pi_out, mu_out, stream);
+    }
+    OGMM_REQUIRE(J <= 8192, OGMM_EUNSUPPORTED, "ogmm_gmm_moments: J=%lld > 8192", (long long)J);
+    const size_t smem = sizeof(float) * ((size_t)(kSmallThreads / 32) * 128 * (kSmallD + 1) + (size_t)J * kSmallD + J);
+    if (smem > 48 * 1024) {
+        int st = cuda_status(cudaFuncSetAttribute(gmm_moments_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  (int)smem), "cudaFuncSetAttribute(gmm_moments_small_kernel)");
+        if (st != OGMM_OK) return st;
+    }
+    gmm_moments_small_kernel<<<(unsigned)B, kSmallThreads, smem, as_stream(stream)>>>(
+        gamma, g_sb, g_sn, g_sj, pts, p_sb, p_sn, p_sd, (int)N, (int)J, (int)D, pi_out, mu_out, sigma_out);
+    OGMM_LAUNCH_CHECK("gmm_moments_small_kernel");
+    return OGMM_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int ogmm_softmax_moments(const float* logits, const float* pts, int64_t p_sb, int64_t p_sn, int64_t p_sd,
+                                    int64_t B, int64_t N, int64_t J, float* gamma_out, float* pi_out, float* mu_out,
+                                    float* sigma_out, ogmm_stream_t stream) {
+    OGMM_REQUIRE(B >= 0 && N >= 1 && J >= 1 && B < (1ll << 31) && N < (1ll << 31), OGMM_EINVAL,
+                 "ogmm_softmax_moments: bad sizes");
+    OGMM_REQUIRE(J <= 1024, OGMM_EUNSUPPORTED, "ogmm_softmax_moments: J=%lld > 1024", (long long)J);
+    if (B == 0) return OGMM_OK;
+    OGMM_REQUIRE(logits && pts && pi_out && mu_out, OGMM_EINVAL, "ogmm_softmax_moments: null pointer");
+    const size_t smem = sizeof(float) * ((size_t)(kSoftThreads / 32) * J * 4 + (size_t)J * 4);
+    if (smem > 48 * 1024) {
+        int st = cuda_status(cudaFuncSetAttribute(softmax_moments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  (int)smem), "cudaFuncSetAttribute(softmax_moments_kernel)");
+        if (st != OGMM_OK) return st;
+    }
+    softmax_moments_kernel<<<(unsigned)B, kSoftThreads, smem, as_stream(stream)>>>(
+        logits, pts, p_sb, p_sn, p_sd, (int)N, (int)J, gamma_out, pi_out, mu_out, sigma_out);
+    OGMM_LAUNCH_CHECK("softmax_moments_kernel");
+    return OGMM_OK;
+}

@@ -1,0 +1,73 @@
+"""nn.Module mirrors of the reference's hot-path modules and DeepGMR's registration function.
+
+  Clustering    models/gmmreg.py:19-29
+  GMMSVD        models/dgcnn.py:90-115
+  graph_features  models/dgcnn.py:135-137 (the kNN + edge-gather opening of DGCNN.forward)
+  gmm_register  baseline/deepgmr.py:17-38
+  deepgmr_em    baseline/deepgmr.py:71-74
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from . import ops
+from .se3 import compute_rigid_transformation
+from .utils import wkeans_plus
+
+__all__ = ["Clustering", "GMMSVD", "graph_features", "gmm_register", "deepgmr_em"]
+
+
+class Clustering(nn.Module):
+    """models/gmmreg.py:19-29: transposed views into wkeans_plus(iters=10, tau=1.0)."""
+
+    def __init__(self, n_clusters):
+        super().__init__()
+        self.n_clusters = n_clusters
+
+    def forward(self, xyz, feats, o_scores):
+        return wkeans_plus(xyz.transpose(-1, -2), feats.transpose(-1, -2), o_scores, self.n_clusters,
+                           iters=10, tau=1.0)
+
+
+class GMMSVD(nn.Module):
+    """models/dgcnn.py:90-115.  ``is_sk=False`` (how models/gmmreg.py:41 builds it) is one fused kernel."""
+
+    def __init__(self, is_sk=True, epsilon=1e-3):
+        super().__init__()
+        self.is_sk = is_sk
+        self.epsilon = epsilon
+
+    @torch.no_grad()
+    def forward(self, src, tgt, src_desc, tgt_desc, src_pi, tgt_pi):
+        batch_size = src.size(0)
+        if not self.is_sk:
+            R, t, src_corr, _ = ops.soft_procrustes(src, tgt, src_desc, tgt_desc, temperature=0.05)
+            return R, t.view(batch_size, 3), src_corr, tgt.transpose(-1, -2)
+        similarity = ops.cos_similarity(src_desc, tgt_desc)
+        scores = ops.sinkhorn(2.0 * (1.0 - similarity), src_pi, tgt_pi, 1e-2, 1e-2, 30)[0]
+        scores = torch.nan_to_num(scores, 1e-4)
+        scores = scores / torch.sum(scores, dim=-1, keepdim=True).clip(min=1e-4)
+        src_corr = torch.einsum('bmd,bnm->bdn', tgt, scores)
+        weight = scores.sum(dim=-1).unsqueeze(1)
+        R, t = compute_rigid_transformation(src.transpose(-1, -2), src_corr, weight)
+        return R, t.view(batch_size, 3), src_corr, tgt.transpose(-1, -2)
+
+
+@torch.no_grad()
+def graph_features(x, k=20):
+    """models/dgcnn.py:135-137 in one launch: x (B,3,N) -> (B,6,N,k) edge tensor fed to conv1."""
+    pts = x.transpose(-1, -2)
+    return ops.knn_graph(pts, pts, k, want_edge=True)[2].permute(0, 3, 1, 2)
+
+
+@torch.no_grad()
+def gmm_register(pi_s, mu_s, mu_t, sigma_t):
+    """baseline/deepgmr.py:17-38 -> (B,4,4); no host SVD and no hard-coded ``.cuda()``."""
+    return ops.gmm_register(pi_s, mu_s, mu_t, sigma_t)
+
+
+@torch.no_grad()
+def deepgmr_em(logits, pts):
+    """baseline/deepgmr.py:71-74 fused: logits (B,J,N), pts (B,3,N) -> gamma (B,J,N), pi, mu, sigma."""
+    return ops.softmax_moments(logits, pts)

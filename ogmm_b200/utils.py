@@ -1,0 +1,139 @@
+"""Drop-in mirror of the reference's ``lib/utils.py`` hot-path functions (same names, signatures,
+argument meaning, return shapes and dtypes), computed by the sm_100a kernels.
+
+Each function cites the reference lines it replaces.  Inputs must be CUDA float32 tensors (views
+are fine); results come back on the same device and stream.  Forward / inference only: outputs do
+not carry autograd history ("Autograd").
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+__all__ = ["square_distance", "knn", "get_graph_feature", "sinkhorn", "index_points", "gmm_params",
+           "og_params", "farthest_point_sample", "cos_similarity", "get_local_corrs", "get_anchor_corrs",
+           "wkeans_plus"]
+
+
+def square_distance(src, dst, normalize=False):
+    """lib/utils.py:12-34.  The dense (B,N,M) matrix, for callers that want it (metrics, losses).
+
+    The hot path never materialises this matrix -- ``knn`` fuses it with the selection -- so this
+    stays a handful of torch ops on the caller's device, in the reference's operation order.
+    """
+    nb, n, _ = src.shape
+    m = dst.shape[1]
+    dist = torch.matmul(src, dst.permute(0, 2, 1)) * -2
+    if normalize:
+        return dist + 2.0
+    dist += torch.sum(src ** 2, -1).view(nb, n, 1)
+    dist += torch.sum(dst ** 2, -1).view(nb, 1, m)
+    return torch.clamp(dist, min=1e-12)
+
+
+@torch.no_grad()
+def knn(src, tgt, k, normalize=False):
+    """lib/utils.py:37-44.  src (B,N,C), tgt (B,M,C) -> int64 (B,N,k), ascending distance.
+
+    Ties resolve to the lowest index (torch.topk's order is unspecified)."""
+    return ops.knn_graph(src, tgt, k, normalize)[0]
+
+
+@torch.no_grad()
+def get_graph_feature(x, k=20, idx=None, extra_dim=False):
+    """lib/utils.py:47-66.  x (B,C,N) -> (B,2C,N,k) view over (B,N,k,2C) memory, [x_j - x_i ; x_i].
+
+    ``idx=None`` runs the fused distance + top-k + gather kernel.  Unlike the reference (:57) a
+    caller-supplied ``idx`` is NOT modified (no reference caller reads it afterwards)."""
+    nb, c, n = x.shape
+    if idx is None:
+        if extra_dim:
+            pts = x[:, 6:].transpose(-1, -2)
+            edge = ops.edge_gather(x, ops.knn_graph(pts, pts, k)[0])
+        else:
+            pts = x.transpose(-1, -2)
+            edge = ops.knn_graph(pts, pts, k, want_edge=True)[2]
+    else:
+        edge = ops.edge_gather(x, idx)
+    return edge.permute(0, 3, 1, 2)
+
+
+@torch.no_grad()
+def sinkhorn(cost, p=None, q=None, epsilon=1e-2, thresh=1e-2, max_iter=100):
+    """lib/utils.py:74-108.  Log-domain Sinkhorn -> (gamma (B,N,M), mean_b sum gamma*cost)."""
+    gamma, loss, _ = ops.sinkhorn(cost, p, q, epsilon, thresh, max_iter)
+    return gamma, loss.mean()
+
+
+def index_points(points, idx):
+    """lib/utils.py:111-127.  points (B,N,C), idx (B,S) -> (B,S,C)."""
+    nb = points.shape[0]
+    view = [nb] + [1] * (idx.dim() - 1)
+    rep = [1] + list(idx.shape[1:])
+    bidx = torch.arange(nb, dtype=torch.long, device=points.device).view(view).repeat(rep)
+    return points[bidx, idx, :]
+
+
+@torch.no_grad()
+def gmm_params(gamma, pts, return_sigma=False):
+    """lib/utils.py:130-149.  gamma (B,N,J), pts (B,N,D) -> pi (B,J), mu (B,J,D) [, sigma (B,J,D,D)]."""
+    return ops.gmm_moments(gamma, pts, return_sigma)
+
+
+@torch.no_grad()
+def og_params(pts, gamma, o_score=None, feature=None):
+    """lib/utils.py:152-167.  Overlap-guided moments with the extra (J+1)-th non-overlap component."""
+    if o_score is not None:
+        score = torch.cat([gamma * o_score.unsqueeze(-1), (1.0 - o_score).unsqueeze(-1)], dim=-1)
+    else:
+        score = gamma
+    pi, mu = ops.gmm_moments(score, pts)
+    if feature is not None:
+        return pi, mu, ops.gmm_moments(score, feature)[1]
+    return pi, mu
+
+
+@torch.no_grad()
+def farthest_point_sample(xyz, npoint, is_center=False):
+    """lib/utils.py:170-198.  xyz (B,N,3) -> int64 (B,npoint).
+
+    ``is_center=False`` draws the start index with the reference's own call
+    (``torch.randint(0, N, (B,), dtype=torch.long)`` on the host, :190) so a seeded run matches."""
+    start = None if is_center else torch.randint(0, xyz.shape[1], (xyz.shape[0],), dtype=torch.long)
+    return ops.fps(xyz, npoint, start)[0]
+
+
+@torch.no_grad()
+def cos_similarity(x, y):
+    """lib/utils.py:222-226.  (B,N,D), (B,M,D) -> (B,N,M)."""
+    return ops.cos_similarity(x, y)
+
+
+@torch.no_grad()
+def get_local_corrs(xyz, xyz_mu, feats):
+    """lib/utils.py:244-254.  Feature of the point nearest to each anchor: 1-NN through the kNN kernel."""
+    idx = ops.knn_graph(xyz_mu, xyz, 1)[0]                       # (B,S,1)
+    return torch.gather(feats, dim=1, index=idx.repeat(1, 1, feats.size(-1)))
+
+
+@torch.no_grad()
+def get_anchor_corrs(xyz, feats, num_clusters, dst='eu', iters=10, is_fast=True):
+    """lib/utils.py:257-266, ``is_fast=True`` branch (the only one the model takes).  xyz (B,3,N), feats (B,D,N)."""
+    if not is_fast:
+        raise NotImplementedError("get_anchor_corrs(is_fast=False) has no live caller in the reference")
+    xt, ft = xyz.transpose(-1, -2), feats.transpose(-1, -2)
+    start = torch.randint(0, xt.shape[1], (xt.shape[0],), dtype=torch.long)
+    ids, xyz_mu = ops.fps(xt, num_clusters, start, want_points=True)
+    feats_pos = index_points(ft, ids).transpose(-1, -2)
+    feats_anchor = get_local_corrs(xt, xyz_mu, ft).transpose(-1, -2)
+    return feats_anchor, feats_pos, xyz_mu.transpose(-1, -2)
+
+
+@torch.no_grad()
+def wkeans_plus(xyz, feats, o_scores, n_clusters, iters=10, tau=1.0):
+    """lib/utils.py:269-291.  xyz (B,N,3), feats (B,N,D) (a view of (B,D,N) is read in place), o (B,N)
+    -> gamma (B,N,J), pi (B,J), node_xyz (B,J,3), node_feats (B,J,D)."""
+    gamma, pi, node_xyz, _ = ops.sinkhorn_cluster(xyz, o_scores, n_clusters, iters=iters, tau=tau)
+    node_feats = ops.gmm_moments(gamma, feats)[1]
+    return gamma, pi, node_xyz, node_feats

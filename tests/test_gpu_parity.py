@@ -1,0 +1,355 @@
+"""GPU parity tests: the CUDA path (through the Python shim -> C ABI) against the CPU oracle and
+against the committed golden fixtures (outputs of the unmodified reference).
+
+Tolerances are BASELINE.json's: kNN index sets bit-exact on decidable rows (same order), GMM
+parameters within 1e-4 relative (scale-relative for centroids), rotation within 1e-3 degree,
+translation within 1e-5 of scene scale -- each checked per stage on identical stage inputs
+("End-to-end tolerances").
+"""
+import numpy as np
+import pytest
+import torch
+
+from gpu_util import decidable_rows, rot_err_deg
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def og():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import ogmm_b200
+    ogmm_b200._lib.load()
+    return ogmm_b200
+
+
+@pytest.fixture(scope="module")
+def orc():
+    from oracle import ogmm_oracle
+    return ogmm_oracle
+
+
+def cu(t):
+    return t.to(DEV)
+
+
+def relerr(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp(min=1e-30))
+
+
+# ------------------------------------------------------------------------------------------ kNN
+def check_knn(og, src, dst, k, normalize=False):
+    idx = og.knn(cu(src), cu(dst), k, normalize).cpu()
+    assert idx.dtype == torch.int64 and tuple(idx.shape) == (src.shape[0], src.shape[1], k)
+    ok, dist = decidable_rows(src, dst, k, normalize)
+    ref = dist.topk(k, dim=-1, largest=False, sorted=True)[1]
+    assert ok.float().mean() > 0.5
+    assert torch.equal(idx[ok], ref[ok]), "decidable rows must match the fp64 order exactly"
+    # undecidable rows: same distances up to the error bound
+    got_d = torch.gather(dist, 2, idx)
+    ref_d = torch.gather(dist, 2, ref)
+    assert float((got_d - ref_d).abs().max()) < 1e-4
+    return idx
+
+
+def test_knn_golden(og, golden):
+    g = golden("knn_xyz")
+    idx = og.knn(cu(g["src"]), cu(g["dst"]), 8).cpu()
+    ok, _ = decidable_rows(g["src"], g["dst"], 8)
+    assert torch.equal(idx[ok], g["idx"][ok])
+    idx20 = og.knn(cu(g["src"]), cu(g["src"]), 20).cpu()
+    ok, _ = decidable_rows(g["src"], g["src"], 20)
+    assert torch.equal(idx20[ok], g["idx_self"][ok])
+    # self is always neighbour 0 up to the clamp tie (distance 1e-12 ties resolve to the lowest index)
+    gc = golden("knn_cosine")
+    idc = og.knn(cu(gc["src"]), cu(gc["src"]), 5, True).cpu()
+    ok, _ = decidable_rows(gc["src"], gc["src"], 5, True)
+    assert torch.equal(idc[ok], gc["idx"][ok])
+
+
+@pytest.mark.parametrize("n,m,k", [(1024, 1024, 20), (717, 717, 20), (300, 1500, 5), (64, 40, 1), (33, 33, 33), (2500, 2500, 16)])
+def test_knn_xyz_sizes(og, n, m, k):
+    g = torch.Generator().manual_seed(n * 7 + m)
+    src = torch.rand(2, n, 3, generator=g) * 2 - 1
+    dst = src if n == m else torch.rand(2, m, 3, generator=g) * 2 - 1
+    check_knn(og, src, dst, k)
+
+
+def test_knn_lattice_known_answer(og):
+    # 6x6x6 unit lattice: the 6 face neighbours of an interior point are at distance 1, the next at sqrt(2)
+    ax = torch.arange(6, dtype=torch.float32)
+    pts = torch.stack(torch.meshgrid(ax, ax, ax, indexing="ij"), -1).reshape(1, -1, 3)
+    idx = og.knn(cu(pts), cu(pts), 7).cpu()[0]
+    center = (2 * 36 + 3 * 6 + 2)
+    nb = set(idx[center].tolist())
+    expect = {center, center - 36, center + 36, center - 6, center + 6, center - 1, center + 1}
+    assert nb == expect and idx[center, 0] == center
+    # ties (all six at distance exactly 1) come back lowest index first
+    assert idx[center, 1:].tolist() == sorted(idx[center, 1:].tolist())
+
+
+def test_knn_strided_views_and_wide(og, golden):
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(2, 3, 512, generator=g)                 # (B,3,N) as the model holds it
+    a = og.knn(cu(x).transpose(-1, -2), cu(x).transpose(-1, -2), 20).cpu()
+    b = og.knn(cu(x.transpose(-1, -2).contiguous()), cu(x.transpose(-1, -2).contiguous()), 20).cpu()
+    assert torch.equal(a, b)
+    w = golden("knn_wide")
+    idx = og.knn(cu(w["src"]), cu(w["src"]), 20).cpu()
+    ok, _ = decidable_rows(w["src"], w["src"], 20)
+    assert ok.float().mean() > 0.9 and torch.equal(idx[ok], w["idx"][ok])
+    for c in (16, 64, 130):
+        f = torch.relu(torch.randn(1, 400, c, generator=g))
+        check_knn(og, f, f, 20)
+
+
+def test_edge_features(og, orc, golden):
+    g = golden("edge_xyz")
+    out = og.get_graph_feature(cu(g["x"]), 8, cu(g["idx"]).clone())
+    assert tuple(out.shape) == tuple(g["feat"].shape) and not out.is_contiguous()
+    assert torch.equal(out.cpu(), g["feat"])                 # pure gather + subtract: bit exact
+    auto = og.get_graph_feature(cu(g["x"]), 5).cpu()
+    ok, _ = decidable_rows(g["x"].transpose(1, 2), g["x"].transpose(1, 2), 5)
+    assert torch.equal(auto.permute(0, 2, 3, 1)[ok], g["feat_auto"].permute(0, 2, 3, 1)[ok])
+    e = golden("edge_extra")
+    extra = og.get_graph_feature(cu(e["x"]), 6, None, True).cpu()
+    ok, _ = decidable_rows(e["x"][:, 6:].transpose(1, 2), e["x"][:, 6:].transpose(1, 2), 6)
+    assert torch.equal(extra.permute(0, 2, 3, 1)[ok], e["feat"].permute(0, 2, 3, 1)[ok])
+    # fused kernel at model size == knn then gather
+    x = torch.rand(3, 3, 1024)
+    fused = og.graph_features(cu(x), 20)
+    idx = og.knn(cu(x).transpose(1, 2), cu(x).transpose(1, 2), 20)
+    assert torch.equal(fused, og.get_graph_feature(cu(x), 20, idx))
+    assert torch.equal(fused.cpu(), orc.edge_features(x, 20, idx.cpu()))
+
+
+# ------------------------------------------------------------------------------------------ FPS
+def test_fps(og, orc, golden):
+    g = golden("fps")
+    assert torch.equal(og.ops.fps(cu(g["xyz"]), 16)[0].cpu(), g["ids_center"])
+    assert torch.equal(og.ops.fps(cu(g["xyz"]), 12, g["start_random"])[0].cpu(), g["ids_random"])
+    torch.manual_seed(99)
+    assert torch.equal(og.farthest_point_sample(cu(g["xyz"]), 12).cpu(), g["ids_random"])
+    for n in (1024, 700, 3000, 5000):
+        x = torch.rand(3, n, 3)
+        assert torch.equal(og.farthest_point_sample(cu(x), 16, True).cpu(), orc.fps_indices(x, 16, True))
+    a = golden("anchors")
+    torch.manual_seed(7)
+    anc, pos, mu = og.get_anchor_corrs(cu(a["xyz"]), cu(a["feats"]), 16)
+    assert torch.equal(pos.cpu(), a["pos"]) and torch.equal(mu.cpu(), a["mu"]) and torch.equal(anc.cpu(), a["anchor"])
+
+
+# ------------------------------------------------------------------------------------------ M-step
+def test_moments_golden(og, golden):
+    g = golden("moments")
+    pi, mu, sigma = og.gmm_params(cu(g["gamma"]), cu(g["xyz"]), True)
+    assert relerr(pi, g["pi"]) < 1e-5 and relerr(mu, g["mu"]) < 1e-5 and relerr(sigma, g["sigma"]) < 1e-5
+    assert tuple(sigma.shape) == (2, 8, 3, 3)
+    mf = og.gmm_params(cu(g["gamma"]), cu(g["feats"]))[1]
+    assert relerr(mf, g["mu_feats"]) < 1e-5
+    opi, omu, ofe = og.og_params(cu(g["xyz"]), cu(g["gamma"]), cu(g["o"]), cu(g["feats"]))
+    assert relerr(opi, g["og_pi"]) < 1e-5 and relerr(omu, g["og_mu"]) < 1e-5 and relerr(ofe, g["og_feats"]) < 1e-5
+
+
+def test_moments_one_hot_known_answer(og):
+    # one-hot gamma -> cluster means (up to the reference's +1e-5 in npi)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2, 600, 3, generator=g)
+    lab = torch.randint(0, 16, (2, 600), generator=g)
+    gamma = torch.nn.functional.one_hot(lab, 16).float()
+    pi, mu = og.gmm_params(cu(gamma), cu(x))
+    for b in range(2):
+        for j in range(16):
+            m = x[b][lab[b] == j]
+            assert abs(float(pi[b, j]) - len(m) / 600) < 1e-6
+            assert torch.allclose(mu[b, j].cpu(), m.sum(0) / (len(m) + 1e-5), atol=1e-5)
+
+
+@pytest.mark.parametrize("n,j,d", [(1024, 16, 512), (717, 16, 512), (1024, 128, 512), (1000, 17, 96), (4096, 64, 256), (128, 8, 40)])
+def test_feature_moments_native_layout(og, orc, n, j, d):
+    g = torch.Generator().manual_seed(n + j + d)
+    gamma = torch.softmax(torch.randn(2, n, j, generator=g) * 3, -1) * torch.rand(2, n, 1, generator=g)
+    feats = torch.relu(torch.randn(2, d, n, generator=g))             # (B,D,N) as the model holds it
+    pi, mu = og.gmm_params(cu(gamma), cu(feats).transpose(-1, -2))
+    rpi, rmu = orc.gmm_moments(gamma.double(), feats.transpose(-1, -2).double())
+    assert relerr(pi, rpi) < 1e-5
+    assert float(((mu.cpu().double() - rmu).abs() / rmu.abs().clamp(min=1e-3)).max()) < 1e-4
+    # row-major (B,N,D) features give the same answer
+    mu2 = og.gmm_params(cu(gamma), cu(feats.transpose(-1, -2).contiguous()))[1]
+    assert relerr(mu2, rmu) < 1e-5
+
+
+def test_deepgmr_em_and_register(og, golden):
+    g = golden("deepgmr")
+    gam, pi, mu, sigma = og.deepgmr_em(cu(g["src_logits"]), cu(g["src"]))
+    assert relerr(gam, g["src_gamma"]) < 1e-5 and relerr(pi, g["src_pi"]) < 1e-5
+    assert relerr(mu, g["src_mu"]) < 1e-5 and relerr(sigma, g["src_sigma"]) < 1e-4
+    # the M-step with sigma through the reference-named function on a transposed view
+    pi2, mu2, sg2 = og.gmm_params(cu(g["src_gamma"]).transpose(-1, -2), cu(g["src"]).transpose(-1, -2), True)
+    assert relerr(pi2, g["src_pi"]) < 1e-5 and relerr(mu2, g["src_mu"]) < 1e-5 and relerr(sg2, g["src_sigma"]) < 1e-4
+    tf = og.gmm_register(cu(g["src_pi"]), cu(g["src_mu"]), cu(g["tgt_mu"]), cu(g["tgt_sigma"])).cpu()
+    assert float(rot_err_deg(tf[:, :3, :3], g["transform"][:, :3, :3]).max()) < 1e-3
+    scale = float(g["tgt_mu"].abs().max())
+    assert float((tf[:, :3, 3] - g["transform"][:, :3, 3]).abs().max()) < 1e-5 * max(scale, 1.0) * 10
+    assert torch.equal(tf[:, 3], g["transform"][:, 3])
+
+
+# ------------------------------------------------------------------------------------------ Sinkhorn
+def test_sinkhorn_golden(og, golden):
+    g = golden("sinkhorn")
+    gam, loss = og.sinkhorn(cu(g["cost"]), p=cu(g["p"]), q=None, max_iter=10)
+    assert relerr(gam, g["gamma10"]) < 1e-4 and abs(float(loss) - float(g["loss10"])) < 1e-5
+    gam, loss = og.sinkhorn(cu(g["cost"]), p=cu(g["p"]), q=None, max_iter=100)
+    assert relerr(gam, g["gamma100"]) < 1e-4
+    gam, loss = og.sinkhorn(cu(g["cost"]), p=None, q=cu(g["q"]), epsilon=1e-2, thresh=1e-2, max_iter=30)
+    assert relerr(gam, g["gamma_q"]) < 1e-4
+
+
+def test_sinkhorn_batch_coupled_early_exit(og, orc, golden):
+    g = golden("sinkhorn")
+    gam, loss, run = og.ops.sinkhorn(cu(g["cost"]), cu(g["p"]), None, 0.5, 1e-2, 50, want_iters=True)
+    _, _, it = orc.sinkhorn_log(g["cost"], g["p"], None, 0.5, 1e-2, 50, return_iters=True)
+    assert it < 50 and int(run[0]) == it, "early exit must stop at the reference's iteration"
+    assert relerr(gam, g["gamma_early"]) < 1e-4 and abs(float(loss.mean()) - float(g["loss_early"])) < 1e-4
+
+
+def check_cluster(og, orc, xyz, feats, o, J, tol_mu=1e-4):
+    tr = []
+    rg, rpi, rmu, rnf = orc.sinkhorn_kmeans(xyz, feats.transpose(-1, -2), o, J, trace=tr)
+    dg, dpi, dmu, dnf = orc.sinkhorn_kmeans(xyz.double(), feats.transpose(-1, -2).double(), o.double(), J)
+    gam, pi, mu, nf = og.wkeans_plus(cu(xyz), cu(feats).transpose(-1, -2), cu(o), J, iters=10, tau=1.0)
+    run = og.ops.sinkhorn_cluster(cu(xyz), cu(o), J, want_iters=True)[3]
+    assert run.cpu().tolist() == tr
+    scale = float(rmu.abs().max())
+    e_mu = float((mu.cpu() - rmu).abs().max()) / scale
+    e_mu64 = float((mu.cpu().double() - dmu).abs().max()) / scale
+    spread = float((rmu.double() - dmu).abs().max()) / scale
+    e_pi = relerr(pi, rpi)
+    e_nf = float((nf.cpu() - rnf).abs().max() / rnf.abs().max())
+    e_g = float((gam.cpu() - rg).abs().max())
+    print(f"cluster parity N={xyz.shape[1]} J={J}: mu {e_mu:.2e} (vs fp64 {e_mu64:.2e}, oracle fp32-fp64 spread {spread:.2e}) "
+          f"pi {e_pi:.2e} feats {e_nf:.2e} gamma abs {e_g:.2e}")
+    assert e_mu < tol_mu and e_pi < 1e-4 and e_nf < 1e-4 and e_g < 1e-3
+    return gam, pi, mu, nf
+
+
+def test_cluster_golden(og, golden):
+    for tag in ("small", "full"):
+        g = golden(f"wkeans_{tag}")
+        gam, pi, mu, nf = og.wkeans_plus(cu(g["xyz"]), cu(g["feats"]).transpose(-1, -2), cu(g["o"]), int(g["J"]))
+        scale = float(g["node_xyz"].abs().max())
+        assert float((mu.cpu() - g["node_xyz"]).abs().max()) / scale < 1e-4
+        assert relerr(pi, g["pi"]) < 1e-4 and relerr(nf, g["node_feats"]) < 1e-4
+        assert float((gam.cpu() - g["gamma"]).abs().max()) < 1e-3
+
+
+@pytest.mark.parametrize("n,j", [(1024, 16), (717, 16), (256, 8), (2048, 32), (1024, 128)])
+def test_cluster_vs_oracle(og, orc, n, j):
+    from ogmm_b200 import synth
+    src, _, _, _ = synth.modelnet_batch(40, 3, n)
+    xyz = torch.from_numpy(src).transpose(1, 2).contiguous()
+    g = torch.Generator().manual_seed(n + j)
+    feats = torch.relu(torch.randn(3, 64, n, generator=g))
+    o = torch.sigmoid(torch.randn(3, n, generator=g))
+    check_cluster(og, orc, xyz, feats, o, j)
+
+
+def test_cluster_metre_scale_and_strided_xyz(og, orc):
+    from ogmm_b200 import synth
+    src, _, _, _ = synth.icl_nuim_batch(3, 2, 1024)
+    x3 = torch.from_numpy(src)                                   # (B,3,N)
+    g = torch.Generator().manual_seed(3)
+    feats = torch.relu(torch.randn(2, 32, 1024, generator=g))
+    o = torch.sigmoid(torch.randn(2, 1024, generator=g))
+    xyz = x3.transpose(1, 2).contiguous()
+    rg, rpi, rmu, rnf = orc.sinkhorn_kmeans(xyz, feats.transpose(-1, -2), o, 16)
+    gam, pi, mu, nf = og.Clustering(16)(cu(x3), cu(feats), cu(o))     # transposed views inside
+    scale = float(rmu.abs().max())
+    assert float((mu.cpu() - rmu).abs().max()) / scale < 1e-4 and relerr(pi, rpi) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------ Procrustes
+def test_procrustes_golden(og, golden):
+    g = golden("procrustes")
+    rot, t = og.compute_rigid_transformation(cu(g["src"]), cu(g["corr"]), cu(g["weight"]))
+    assert tuple(rot.shape) == (6, 3, 3) and tuple(t.shape) == (6, 3, 1)
+    err = rot_err_deg(rot.cpu(), g["rot"])
+    assert float(err.max()) < 1e-3, err
+    scale = float(g["corr"].abs().max())
+    assert float((t.cpu() - g["t"]).abs().max()) < 1e-5 * scale
+    assert torch.all(torch.det(rot.cpu().double()) > 0.999)
+
+
+def test_procrustes_exact_motion_known_answer(og):
+    g = torch.Generator().manual_seed(11)
+    src = torch.randn(64, 3, 40, generator=g)
+    q, _ = torch.linalg.qr(torch.randn(64, 3, 3, generator=g))
+    q = q * torch.sign(torch.det(q))[:, None, None]
+    tr = torch.randn(64, 3, 1, generator=g)
+    corr = q @ src + tr
+    w = torch.rand(64, 1, 40, generator=g) + 0.1
+    rot, t = og.compute_rigid_transformation(cu(src), cu(corr), cu(w))
+    assert float(rot_err_deg(rot.cpu(), q).max()) < 1e-3
+    assert float((t.cpu() - tr).abs().max()) < 1e-4
+    # strided inputs (transposed views) go through the same kernel
+    rot2, _ = og.compute_rigid_transformation(cu(src.transpose(1, 2).contiguous()).transpose(1, 2), cu(corr), cu(w))
+    assert torch.equal(rot, rot2)
+
+
+def test_gmmsvd_golden(og, golden):
+    g = golden("gmmsvd")
+    head = og.GMMSVD(False)
+    rot, t, corr, tt = head(cu(g["src"]), cu(g["tgt"]), cu(g["src_desc"]), cu(g["tgt_desc"]), cu(g["src_pi"]), cu(g["tgt_pi"]))
+    assert float(rot_err_deg(rot.cpu(), g["rot"]).max()) < 1e-3
+    scale = float(g["tgt"].abs().max())
+    assert float((t.cpu() - g["t"]).abs().max()) < 1e-5 * scale * 10
+    assert relerr(corr, g["corr"]) < 1e-4 and torch.equal(tt.cpu(), g["tgt_t"])
+    sim = og.cos_similarity(cu(g["src_desc"]), cu(g["tgt_desc"]))
+    assert float((sim.cpu() - g["sim"]).abs().max()) < 1e-6
+    rot, t, corr, _ = og.GMMSVD(True)(cu(g["src"]), cu(g["tgt"]), cu(g["src_desc"]), cu(g["tgt_desc"]), cu(g["src_pi"]), cu(g["tgt_pi"]))
+    assert float(rot_err_deg(rot.cpu(), g["rot_sk"]).max()) < 1e-2
+    assert relerr(corr, g["corr_sk"]) < 1e-3
+
+
+@pytest.mark.parametrize("j,d", [(16, 512), (64, 512), (128, 512), (10, 33)])
+def test_gmmsvd_sizes(og, orc, j, d):
+    g = torch.Generator().manual_seed(j * d)
+    mu_s = torch.randn(4, j, 3, generator=g)
+    q, _ = torch.linalg.qr(torch.randn(4, 3, 3, generator=g))
+    q = q * torch.sign(torch.det(q))[:, None, None]
+    mu_t = (q @ mu_s.transpose(1, 2)).transpose(1, 2).contiguous() + 0.3
+    ds = torch.relu(torch.randn(4, j, d, generator=g))
+    dt = ds + 0.02 * torch.randn(4, j, d, generator=g)
+    rr, rt, rc, _ = orc.soft_svd_head(mu_s, mu_t, ds, dt)
+    rot, t, corr, _ = og.GMMSVD(False)(cu(mu_s), cu(mu_t), cu(ds), cu(dt), None, None)
+    assert float(rot_err_deg(rot.cpu(), rr).max()) < 1e-3
+    assert relerr(corr, rc) < 1e-4 and float((t.cpu() - rt).abs().max()) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------ full size
+def test_full_size_properties(og):
+    """BASELINE.json config 2 size (B=256 pairs, N=1024, J=16): size-independent properties."""
+    from ogmm_b200 import synth
+    h = synth.hot_path_inputs(0, 256, 1024, 512, tile=8)
+    src, tgt = cu(torch.from_numpy(h["src"])), cu(torch.from_numpy(h["tgt"]))
+    edge = og.graph_features(src, 20)
+    assert tuple(edge.shape) == (256, 6, 1024, 20)
+    # x_i channel equals the point itself; neighbour 0 is the point (distance clamp tie -> lowest index may differ on duplicates)
+    assert torch.equal(edge[:, 3:, :, 0], src)
+    # tiled inputs give identical outputs (determinism across CTAs)
+    assert torch.equal(edge[0], edge[8])
+    gam, pi, mu, nf = og.Clustering(16)(src, cu(torch.from_numpy(h["src_feats"])), cu(torch.from_numpy(h["src_o"])))
+    assert torch.isfinite(gam).all() and torch.equal(gam[0], gam[8]) and torch.equal(nf[1], nf[9])
+    # pi is the column mean of gamma; mu the gamma-weighted mean (M-step identities)
+    assert torch.allclose(pi, gam.mean(1), rtol=1e-5, atol=1e-8)
+    ref_mu = gam.transpose(1, 2) @ src.transpose(1, 2) / (pi * 1024 + 1e-5).unsqueeze(-1)
+    assert float((mu - ref_mu).abs().max()) < 1e-5
+    gam_t, pi_t, mu_t, nf_t = og.Clustering(16)(tgt, cu(torch.from_numpy(h["tgt_feats"])), cu(torch.from_numpy(h["tgt_o"])))
+    rot, t, corr, _ = og.GMMSVD(False)(mu, mu_t, nf, nf_t, pi, pi_t)
+    assert torch.allclose(torch.det(rot), torch.ones(256, device=DEV), atol=1e-5)
+    eye = torch.eye(3, device=DEV).expand(256, 3, 3)
+    assert float((rot @ rot.transpose(1, 2) - eye).abs().max()) < 1e-5
