@@ -46,13 +46,20 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     procs = []
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    headers.append(os.path.join(os.path.dirname(HERE), "include", "ogmm_b200.h"))
+    newest_header = max(os.path.getmtime(h) for h in headers)
+    objs = []
     for src in SOURCES:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        if (not force and os.path.exists(obj)
+                and os.path.getmtime(obj) > max(newest_header, os.path.getmtime(os.path.join(CSRC, src)))):
+            objs.append(obj)          # up to date
+            continue
         cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-    objs = []
     for src, obj, p in procs:
         out, _ = p.communicate()
         if p.returncode != 0:

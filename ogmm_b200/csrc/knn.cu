@@ -45,16 +45,19 @@ struct TopK {
             ++cnt;
         }
     }
+    // Sorted insert.  Up to the insertion point the comparison is strict (an equal, earlier entry stays in
+    // front); from there on every entry shifts down by one, so ties keep their arrival (= index) order.
     __device__ __forceinline__ void insert(float v, int idx) {
+        bool moved = false;
 #pragma unroll
         for (int j = 0; j < K; ++j) {
-            const bool lt = v < d[j];
+            moved = moved || (v < d[j]);
             const float td = d[j];
             const int ti = i[j];
-            d[j] = lt ? v : td;
-            i[j] = lt ? idx : ti;
-            v = lt ? td : v;
-            idx = lt ? ti : idx;
+            d[j] = moved ? v : td;
+            i[j] = moved ? idx : ti;
+            v = moved ? td : v;
+            idx = moved ? ti : idx;
         }
     }
     // Warp-converged: every lane of the calling warp must call merge() together.
