@@ -1,29 +1,44 @@
 // K2: farthest-point init + overlap-guided Sinkhorn k-means, and the stand-alone Sinkhorn (sm_100a).
 //
-// One CTA per cloud; every point lives in the registers of one thread for the whole
-// 10 x 10 iteration loop (lib/utils.py:269-288), so the only HBM traffic is the algorithmic
-// one: xyz + overlap scores in, gamma / pi / mu out.  The cost matrix is never stored: a cost
-// c_ij is recomputed from the point (registers) and the centroid (shared memory) where needed.
+// One CTA per cloud; every point lives in the registers of one thread for the whole 10 x 10
+// iteration loop (lib/utils.py:269-288), so the only HBM traffic is the algorithmic one: xyz +
+// overlap scores in, gamma / pi / mu out.
 //
 // Reference arithmetic reproduced here
 //   FPS init             lib/utils.py:170-198 (is_center branch :183-188)
 //   cost                 lib/utils.py:280  torch.cdist -> ATen _euclidean_dist (matmul form, K=5),
 //                        clamp_min(0).sqrt(), .clip(0) / tau
-//   Sinkhorn             lib/utils.py:69-108 log domain; row LSE over j, column LSE over i
+//   Sinkhorn             lib/utils.py:69-108; row normalisation over j, column normalisation over i
 //   early exit           lib/utils.py:99-102 BATCH mean of sum|du|+sum|dv| < thresh (see below)
 //   post                 lib/utils.py:282 nan_to_num, :287 gamma / clip(sum_j gamma, 1e-3)
 //   M-step (xyz)         lib/utils.py:130-140
 //
-// Batch-coupled early exit without a host sync.  Iteration counts couple the clouds of one call
-// only through the exit test.  Launch 0 runs every Sinkhorn call for max_iter iterations and each
-// CTA records its cloud's change per (outer, inner) iteration; the last CTA to finish evaluates the
-// batch means in order and, at the first (outer o, inner i) with mean < thresh and i+1 below the
-// count that was run, stores n_inner[o] = i+1 and resume = o.  Follow-up launches (queued
-// unconditionally; they return at once when resume == iters) restart from the centroids saved at
-// the start of outer iteration `resume`.  Each follow-up certifies at least one more outer
-// iteration, so `iters` follow-ups always suffice.  Results are bit-identical to running the exit
-// test inline, and deterministic (fixed-order reductions, no float atomics).
+// Two arithmetic paths for the inner Sinkhorn iterations:
+//
+//  * scaled domain (kFast; J <= 16, N <= 1024).  For one Sinkhorn call the thread keeps
+//    G_ij = exp(-(c_ij - m_i)/eps), m_i = min_j c_ij, for its points in REGISTERS and iterates on the
+//    scalings  r_i = sum_j G_ij b_j, a_i = (p_i+1e-8)/r_i, s_j = sum_i G_ij a_i, b_j = (q_j+1e-8)/s_j
+//    with FMAs only: one exp per (i,j) per call instead of two per iteration.  In exact arithmetic this
+//    IS the reference's log-domain update (u_i = m_i + eps log a_i, v_j = eps log b_j); in fp32 it agrees
+//    with the fp32 reference to within the reference's own fp32-vs-fp64 spread
+//    (tools/sinkhorn_scaled_emulation.py).  A monitor (every s_j in [1e-30, 1e30], max b / min b <= 1e24)
+//    guards the dynamic range; if it ever trips, that Sinkhorn call is redone in the log domain.
+//  * log domain (generic J, N <= 8192; also the rescue path).  exp2/log2 with a max shift on rows;
+//    column sums need no shift after a row update (every K_ij <= log(p_i+1e-8) < 0) and a column whose
+//    sum underflows is redone with an exact shift.  Costs are recomputed from registers + shared memory.
+//
+// Batch-coupled early exit without a host sync.  Iteration counts couple the clouds of one call only
+// through the exit test.  The main launch runs every Sinkhorn call for max_iter iterations and records
+// each cloud's change per (outer, inner) iteration; the last CTA to finish evaluates the batch means in
+// order and, at the first (outer o, inner i) with mean < thresh and i+1 below the count that was run,
+// stores n_inner[o] = i+1 and resume = o.  ONE follow-up launch is always queued: a persistent
+// cooperative kernel that returns at once when nothing has to change (the common case) and otherwise
+// re-runs from the centroids saved at the start of outer iteration `resume`, re-evaluates, and repeats
+// behind a grid barrier until the schedule is certified.  The result is bit-identical to running the
+// exit test inline, and deterministic (fixed-order reductions, no float atomics).
 #pragma once
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace ogmm {
@@ -37,7 +52,7 @@ struct ClusterWsLayout {
 __host__ __device__ inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 __host__ __device__ inline ClusterWsLayout cluster_ws_layout(int64_t B, int64_t J, int64_t iters, int64_t max_iter) {
     ClusterWsLayout l;
-    l.state_off = 0;                                         // int32[16]: [0]=resume  [1]=done counter
+    l.state_off = 0;                                         // int32[16]: [0]=resume [1]=done counter [2]=rescues
     l.ninner_off = 64;                                       // int32[iters]
     l.means_off = align_up(l.ninner_off + 4 * iters, 256);   // float[iters][max_iter] batch means
     l.diffs_off = align_up(l.means_off + 4 * iters * max_iter, 256);   // float[iters][max_iter][B]
@@ -46,17 +61,50 @@ __host__ __device__ inline ClusterWsLayout cluster_ws_layout(int64_t B, int64_t 
     return l;
 }
 
+__device__ __forceinline__ float sq3(float x, float y, float z) {
+    return __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+}
+__device__ __forceinline__ unsigned long long far_key(float best, int i) {
+    return ((unsigned long long)__float_as_uint(best) << 32) | (0xffffffffu - (unsigned)i);
+}
+
 // ---- farthest point sampling on register-resident points ----------------------------------------
-// lib/utils.py:191-197.  `far` is the first index; writes `npoint` indices through `emit`.
+// One relaxation against centre (cx,cy,cz) followed by the block-wide arg-max (lowest index on ties).
+template <int NT, int PPT>
+__device__ __forceinline__ int fps_relax(const float (&px)[PPT], const float (&py)[PPT], const float (&pz)[PPT],
+                                         float (&best)[PPT], int N, float cx, float cy, float cz,
+                                         unsigned long long* s_key) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = NT / 32;
+    unsigned long long key = 0ull;
+#pragma unroll
+    for (int p = 0; p < PPT; ++p) {
+        const int i = tid + p * NT;
+        if (i < N) {
+            const float d = sq3(px[p] - cx, py[p] - cy, pz[p] - cz);      // sum((xyz - c) ** 2, -1): no FMA
+            if (d < best[p]) best[p] = d;
+            const unsigned long long k = far_key(best[p], i);
+            key = k > key ? k : key;
+        }
+    }
+    key = warp_max_u64(key);
+    __syncthreads();                       // previous readers of s_key are done
+    if (lane == 0) s_key[warp] = key;
+    __syncthreads();
+    unsigned long long k2 = lane < NW ? s_key[lane] : 0ull;
+    k2 = warp_max_u64(k2);
+    return (int)(0xffffffffu - (unsigned)(k2 & 0xffffffffull));
+}
+
+// lib/utils.py:191-197.  `far` is the first index; `emit(s, far)` is called for each of the npoint picks.
 template <int NT, int PPT, typename Emit>
 __device__ __forceinline__ void fps_run(const float (&px)[PPT], const float (&py)[PPT], const float (&pz)[PPT],
                                         float (&best)[PPT], int N, int npoint, int far, float* s_pick,
                                         unsigned long long* s_key, Emit emit) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NW = NT / 32;
+    const int tid = threadIdx.x;
     for (int s = 0; s < npoint; ++s) {
         emit(s, far);
-        // broadcast the coordinates of point `far`
+        __syncthreads();                   // previous readers of s_pick are done
         if ((far % NT) == tid) {
             const int slot = far / NT;
 #pragma unroll
@@ -64,27 +112,22 @@ __device__ __forceinline__ void fps_run(const float (&px)[PPT], const float (&py
                 if (p == slot) { s_pick[0] = px[p]; s_pick[1] = py[p]; s_pick[2] = pz[p]; }
         }
         __syncthreads();
-        const float cx = s_pick[0], cy = s_pick[1], cz = s_pick[2];
-        unsigned long long key = 0ull;
-#pragma unroll
-        for (int p = 0; p < PPT; ++p) {
-            const int i = tid + p * NT;
-            if (i < N) {
-                float dx = px[p] - cx, dy = py[p] - cy, dz = pz[p] - cz;
-                float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-                if (d < best[p]) best[p] = d;
-                unsigned long long k = ((unsigned long long)__float_as_uint(best[p]) << 32) | (0xffffffffu - (unsigned)i);
-                key = k > key ? k : key;
-            }
-        }
-        key = warp_max_u64(key);
-        if (lane == 0) s_key[warp] = key;
-        __syncthreads();
-        unsigned long long k2 = lane < NW ? s_key[lane] : 0ull;
-        k2 = warp_max_u64(k2);
-        far = (int)(0xffffffffu - (unsigned)(k2 & 0xffffffffull));
-        // s_key / s_pick are rewritten only after the next __syncthreads pair
+        far = fps_relax<NT, PPT>(px, py, pz, best, N, s_pick[0], s_pick[1], s_pick[2], s_key);
     }
+}
+
+// First index for is_center=True (:183-188): relax against the centroid, take the farthest point.
+template <int NT, int PPT>
+__device__ __forceinline__ int fps_center_start(const float (&px)[PPT], const float (&py)[PPT], const float (&pz)[PPT],
+                                                float (&best)[PPT], int N, float* s_red, unsigned long long* s_key) {
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+#pragma unroll
+    for (int p = 0; p < PPT; ++p)
+        if ((int)threadIdx.x + p * NT < N) { sx += px[p]; sy += py[p]; sz += pz[p]; }
+    const float cx = block_sum<NT>(sx, s_red) / (float)N;
+    const float cy = block_sum<NT>(sy, s_red) / (float)N;
+    const float cz = block_sum<NT>(sz, s_red) / (float)N;
+    return fps_relax<NT, PPT>(px, py, pz, best, N, cx, cy, cz, s_key);
 }
 
 template <int NT, int PPT>
@@ -97,44 +140,16 @@ fps_kernel(const float* __restrict__ xyz, int64_t sb, int64_t sn, int64_t sc, in
     const int b = blockIdx.x, tid = threadIdx.x;
     const float* base = xyz + (int64_t)b * sb;
     float px[PPT], py[PPT], pz[PPT], best[PPT];
-    float sx = 0.f, sy = 0.f, sz = 0.f;
 #pragma unroll
     for (int p = 0; p < PPT; ++p) {
         const int i = tid + p * NT;
         px[p] = py[p] = pz[p] = 0.f;
         best[p] = 1e10f;
-        if (i < N) {
-            px[p] = base[(int64_t)i * sn]; py[p] = base[(int64_t)i * sn + sc]; pz[p] = base[(int64_t)i * sn + 2 * sc];
-            sx += px[p]; sy += py[p]; sz += pz[p];
-        }
+        if (i < N) { px[p] = base[(int64_t)i * sn]; py[p] = base[(int64_t)i * sn + sc]; pz[p] = base[(int64_t)i * sn + 2 * sc]; }
     }
     int far;
-    if (start == nullptr) {
-        // is_center: relax against the centroid first, start from the farthest point (:183-188)
-        const float cx = block_sum<NT>(sx, s_red) / (float)N;
-        const float cy = block_sum<NT>(sy, s_red) / (float)N;
-        const float cz = block_sum<NT>(sz, s_red) / (float)N;
-        unsigned long long key = 0ull;
-#pragma unroll
-        for (int p = 0; p < PPT; ++p) {
-            const int i = tid + p * NT;
-            if (i < N) {
-                float dx = px[p] - cx, dy = py[p] - cy, dz = pz[p] - cz;
-                float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-                if (d < best[p]) best[p] = d;
-                unsigned long long k = ((unsigned long long)__float_as_uint(best[p]) << 32) | (0xffffffffu - (unsigned)i);
-                key = k > key ? k : key;
-            }
-        }
-        key = warp_max_u64(key);
-        __syncthreads();
-        if ((tid & 31) == 0) s_key[tid >> 5] = key;
-        __syncthreads();
-        unsigned long long k2 = (tid & 31) < NT / 32 ? s_key[tid & 31] : 0ull;
-        k2 = warp_max_u64(k2);
-        far = (int)(0xffffffffu - (unsigned)(k2 & 0xffffffffull));
-        __syncthreads();
-    } else {
+    if (start == nullptr) far = fps_center_start<NT, PPT>(px, py, pz, best, N, s_red, s_key);
+    else {
         far = (int)start[b];
         far = far < 0 ? 0 : (far >= N ? N - 1 : far);
     }
@@ -151,81 +166,206 @@ fps_kernel(const float* __restrict__ xyz, int64_t sb, int64_t sn, int64_t sc, in
     });
 }
 
-// ---- cost sources -----------------------------------------------------------------------------------
-// Cluster mode: c_ij = cdist(x_i, node_j) / tau from registers + shared memory.
-struct NodeCost {
-    const float4* node;     // shared: (x, y, z, |n|^2) per centroid
-    float inv_tau_is_one;   // tau == 1 -> skip the division (x / 1 == x)
-    float tau;
-    __device__ __forceinline__ float operator()(float m2x, float m2y, float m2z, float pn, int j) const {
-        const float4 c = node[j];
-        // ATen _euclidean_dist: [-2x, |x|^2, 1] . [y, 1, |y|^2], accumulated in k order
-        float d2 = __fmul_rn(m2x, c.x);
-        d2 = fmaf(m2y, c.y, d2);
-        d2 = fmaf(m2z, c.z, d2);
-        d2 = __fadd_rn(d2, pn);
-        d2 = __fadd_rn(d2, c.w);
-        float d = sqrtf(fmaxf(d2, 0.f));
-        d = fmaxf(d, 0.f);
-        return inv_tau_is_one != 0.f ? d : __fdiv_rn(d, tau);
-    }
-};
+// ---- cost ------------------------------------------------------------------------------------------------
+// c_ij = cdist(x_i, node_j).clip(0) / tau.  ATen _euclidean_dist: [-2x, |x|^2, 1] . [y, 1, |y|^2] in k order.
+__device__ __forceinline__ float node_cost(float m2x, float m2y, float m2z, float pn, const float4 c, float tau) {
+    float d2 = __fmul_rn(m2x, c.x);
+    d2 = fmaf(m2y, c.y, d2);
+    d2 = fmaf(m2z, c.z, d2);
+    d2 = __fadd_rn(d2, pn);
+    d2 = __fadd_rn(d2, c.w);
+    const float d = fmaxf(sqrtf(fmaxf(d2, 0.f)), 0.f);
+    return tau == 1.0f ? d : __fdiv_rn(d, tau);
+}
 
 struct SinkhornParams {
-    // geometry / marginals
-    const float* xyz; int64_t sb, sn, sc;      // cluster mode
+    const float* xyz; int64_t sb, sn, sc;      // cluster mode: (B,N,3) view
     const float* o_scores;                     // cluster mode (B,N)
     const float* cost;                         // matrix mode (B,N,J)
     const float* p;                            // matrix mode (B,N) or null
     const float* q;                            // matrix mode (B,J) or null
     int B, N, J, iters, max_iter;
     float tau, eps, thresh;
-    // outputs
     float* gamma; float* pi; float* mu; float* loss; int32_t* iters_run;
-    // workspace
     int32_t* state; int32_t* n_inner; float* means; float* diffs; float* hist;
-    int launch;
 };
 
-// Shared memory carve-up (floats): node float4[Jp] | v[Jp] | logq[Jp] | wtot[4][NW][Jp] (one plane in
-// the Sinkhorn loop, four in the M-step) | red[32] | du[32] | tmp[32] | misc[16] | key u64[32]
+// Shared memory of one CTA.
+struct Smem {
+    float4* node;             // [Jp]  centroid (x, y, z, |n|^2)
+    float* v;                 // [Jp]  column potential (log domain) / eps log b (fast path)
+    float* logq;              // [Jp]
+    float* bq;                // [Jp]  fast path: b_j
+    float* wtot;              // [4][NW][Jp] per-warp column totals
+    float* red;               // [32]  block_sum scratch
+    float* du;                // [32]  per-warp sum |du|
+    float* tmp;               // [32]
+    float* misc;              // [16]  [0..2] FPS pick, [5] last-CTA flag, [6] monitor flag
+    unsigned long long* key;  // [32]
+};
 template <int NT>
 __host__ __device__ inline size_t sinkhorn_smem(int J) {
     const int Jp = (J + kJC - 1) / kJC * kJC;
-    return sizeof(float) * ((size_t)4 * Jp + Jp + Jp + (size_t)(NT / 32) * Jp * 4 + 32 + 32 + 32 + 16) +
+    return sizeof(float) * ((size_t)4 * Jp + 3 * (size_t)Jp + (size_t)(NT / 32) * Jp * 4 + 32 + 32 + 32 + 16) +
            sizeof(unsigned long long) * 32;
 }
+template <int NT>
+__device__ __forceinline__ Smem carve_smem(unsigned char* raw, int Jp) {
+    Smem s;
+    s.node = reinterpret_cast<float4*>(raw);
+    s.v = reinterpret_cast<float*>(s.node + Jp);
+    s.logq = s.v + Jp;
+    s.bq = s.logq + Jp;
+    s.wtot = s.bq + Jp;
+    s.red = s.wtot + (size_t)(NT / 32) * Jp * 4;
+    s.du = s.red + 32;
+    s.tmp = s.du + 32;
+    s.misc = s.tmp + 32;
+    s.key = reinterpret_cast<unsigned long long*>(s.misc + 16);
+    return s;
+}
 
-template <int NT, int PPT, bool kCluster>
-__global__ void __launch_bounds__(NT)
-sinkhorn_kernel(SinkhornParams P) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+// ---- log-domain Sinkhorn iterations for one call ----------------------------------------------------------
+// u[] (registers) and S.v (shared) start at 0; runs n_it iterations; records the change of each iteration.
+template <int NT, int PPT, typename CostAt>
+__device__ __forceinline__ void ld_iterations(const SinkhornParams& P, const Smem& S, int b, int o, int n_it,
+                                              const float (&logp)[PPT], float (&u)[PPT], CostAt cost_at) {
     constexpr int NW = NT / 32;
+    const int N = P.N, J = P.J, Jp = (J + kJC - 1) / kJC * kJC;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float k2 = (1.0f / P.eps) * kLog2e;
+#pragma unroll
+    for (int p = 0; p < PPT; ++p) u[p] = 0.f;
+    __syncthreads();
+    for (int j = tid; j < Jp; j += NT) S.v[j] = 0.f;
+    __syncthreads();
+
+    for (int it = 0; it < n_it; ++it) {
+        // ---- row update: u_i += eps * (log p_i - LSE_j K_ij)
+        float du_abs = 0.f;
+#pragma unroll
+        for (int p = 0; p < PPT; ++p) {
+            if (tid + p * NT < N) {
+                float m = -INFINITY, s = 0.f;
+                for (int j0 = 0; j0 < J; j0 += kJC) {
+                    float x[kJC];
+                    float mc = -INFINITY;
+#pragma unroll
+                    for (int jj = 0; jj < kJC; ++jj) {
+                        const int j = j0 + jj;
+                        if (j < J) {
+                            x[jj] = __fadd_rn(__fadd_rn(-cost_at(p, j), u[p]), S.v[j]) * k2;
+                            mc = fmaxf(mc, x[jj]);
+                        } else x[jj] = -INFINITY;
+                    }
+                    const float mn = fmaxf(m, mc);
+                    float acc = 0.f;
+#pragma unroll
+                    for (int jj = 0; jj < kJC; ++jj) acc += exp2f(x[jj] - mn);
+                    s = s * exp2f(m - mn) + acc;        // m == -inf on the first chunk -> s * 0
+                    m = mn;
+                }
+                const float lse = (m + log2f(s)) * kLn2;
+                const float un = __fadd_rn(__fmul_rn(P.eps, logp[p] - lse), u[p]);
+                du_abs += fabsf(un - u[p]);
+                u[p] = un;
+            }
+        }
+        // ---- column update: v_j += eps * (log q_j - LSE_i K_ij); no max shift needed after a row update
+        for (int j0 = 0; j0 < J; j0 += kJC) {
+            float part[kJC];
+#pragma unroll
+            for (int jj = 0; jj < kJC; ++jj) part[jj] = 0.f;
+#pragma unroll
+            for (int p = 0; p < PPT; ++p) {
+                if (tid + p * NT < N) {
+#pragma unroll
+                    for (int jj = 0; jj < kJC; ++jj) {
+                        const int j = j0 + jj;
+                        if (j < J) part[jj] += exp2f(__fadd_rn(__fadd_rn(-cost_at(p, j), u[p]), S.v[j]) * k2);
+                    }
+                }
+            }
+            const float tot = butterfly16(part, lane);
+            if ((lane & 1) == 0) S.wtot[warp * Jp + j0 + ((lane >> 1) & 15)] = tot;
+        }
+        du_abs = warp_sum(du_abs);
+        if (lane == 0) S.du[warp] = du_abs;
+        __syncthreads();
+        // final column sums (fixed order over warps) -> staged new v in wtot[j] (warp-0 row, which only this
+        // thread reads); NaN marks a column that must be redone with a max shift
+        int need_exact = 0;
+        for (int j = tid; j < J; j += NT) {
+            float sj = 0.f;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) sj += S.wtot[w * Jp + j];
+            if (sj > 1e-30f && sj < INFINITY) {
+                S.wtot[j] = __fadd_rn(__fmul_rn(P.eps, S.logq[j] - logf(sj)), S.v[j]);
+            } else {
+                S.wtot[j] = NAN;
+                need_exact = 1;
+            }
+        }
+        if (__syncthreads_or(need_exact)) {
+            for (int j = 0; j < J; ++j) {
+                if (S.wtot[j] == S.wtot[j]) continue;               // block-uniform (shared value)
+                float mx = -INFINITY;
+#pragma unroll
+                for (int p = 0; p < PPT; ++p)
+                    if (tid + p * NT < N) mx = fmaxf(mx, __fadd_rn(__fadd_rn(-cost_at(p, j), u[p]), S.v[j]) * k2);
+                mx = warp_max(mx);
+                if (lane == 0) S.tmp[warp] = mx;
+                __syncthreads();
+                float mall = -INFINITY;
+                for (int w = 0; w < NW; ++w) mall = fmaxf(mall, S.tmp[w]);
+                float sm = 0.f;
+#pragma unroll
+                for (int p = 0; p < PPT; ++p)
+                    if (tid + p * NT < N) sm += exp2f(__fadd_rn(__fadd_rn(-cost_at(p, j), u[p]), S.v[j]) * k2 - mall);
+                sm = block_sum<NT>(sm, S.red);
+                if (tid == 0) {
+                    const float lse = (mall + log2f(sm)) * kLn2;
+                    S.wtot[j] = __fadd_rn(__fmul_rn(P.eps, S.logq[j] - lse), S.v[j]);
+                }
+                __syncthreads();
+            }
+        }
+        // commit v, sum |dv|, record this iteration's change
+        float dv_abs = 0.f;
+        for (int j = tid; j < J; j += NT) {
+            const float vn = S.wtot[j];
+            dv_abs += fabsf(vn - S.v[j]);
+            S.v[j] = vn;
+        }
+        dv_abs = warp_sum(dv_abs);
+        if (lane == 0) S.tmp[warp] = dv_abs;
+        __syncthreads();
+        if (tid == 0) {
+            float du = 0.f, dv = 0.f;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) { du += S.du[w]; dv += S.tmp[w]; }
+            P.diffs[((int64_t)o * P.max_iter + it) * P.B + b] = du + dv;
+        }
+        __syncthreads();
+    }
+}
+
+// ---- one cloud, outer iterations resume..iters-1 -----------------------------------------------------------
+// `first`: main launch (every call runs max_iter inner iterations); otherwise counts come from P.n_inner.
+template <int NT, int PPT, bool kCluster, bool kFast>
+__device__ __forceinline__ void process_cloud(const SinkhornParams& P, const Smem& S, int b, int resume, bool first) {
+    constexpr int NW = NT / 32;
+    constexpr int JF = 16;                              // fast path register tile width
     const int N = P.N, J = P.J;
     const int Jp = (J + kJC - 1) / kJC * kJC;
-    float4* s_node = reinterpret_cast<float4*>(smem_raw);
-    float* s_v = reinterpret_cast<float*>(s_node + Jp);
-    float* s_logq = s_v + Jp;
-    float* s_wtot = s_logq + Jp;                         // [NW][Jp] x 4 planes
-    float* s_red = s_wtot + (size_t)NW * Jp * 4;         // block_sum scratch
-    float* s_du = s_red + 32;                            // per-warp sum |du|
-    float* s_tmp = s_du + 32;                            // per-warp scratch (sum |dv|, column max)
-    float* s_misc = s_tmp + 32;                          // [0..3] FPS pick, [5] last-CTA flag
-    unsigned long long* s_key = reinterpret_cast<unsigned long long*>(s_misc + 16);
-
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int iters = P.iters, max_iter = P.max_iter;
+    const float k2 = (1.0f / P.eps) * kLog2e;
 
-    int resume = 0;
-    if (P.launch > 0) {
-        resume = P.state[0];
-        if (resume >= iters) return;
-    }
-
-    // ---- load this cloud's points into registers ---------------------------------------------------
+    // ---- this cloud's points -------------------------------------------------------------------------------
     float m2x[PPT], m2y[PPT], m2z[PPT], pn[PPT], logp[PPT], u[PPT];
     float px[PPT], py[PPT], pz[PPT];
-    const float k2 = (1.0f / P.eps) * kLog2e;      // exponent scale for exp2
+    __syncthreads();
     if constexpr (kCluster) {
         const float* base = P.xyz + (int64_t)b * P.sb;
         float osum = 0.f;
@@ -240,223 +380,232 @@ sinkhorn_kernel(SinkhornParams P) {
                 osum += logp[p];
             }
             m2x[p] = -2.f * px[p]; m2y[p] = -2.f * py[p]; m2z[p] = -2.f * pz[p];
-            pn[p] = __fadd_rn(__fadd_rn(__fmul_rn(px[p], px[p]), __fmul_rn(py[p], py[p])), __fmul_rn(pz[p], pz[p]));
+            pn[p] = sq3(px[p], py[p], pz[p]);
         }
-        // lib/utils.py:276  o / clip(sum o, 1e-4); then log(p + 1e-8) (:92)
-        osum = fmaxf(block_sum<NT>(osum, s_red), 1e-4f);
+        // lib/utils.py:276  o / clip(sum o, 1e-4); logp holds p_i + 1e-8 (fast) or its log (log domain, :92)
+        osum = fmaxf(block_sum<NT>(osum, S.red), 1e-4f);
 #pragma unroll
-        for (int p = 0; p < PPT; ++p) logp[p] = logf(__fdiv_rn(logp[p], osum) + 1e-8f);
-        for (int j = tid; j < Jp; j += NT) s_logq[j] = logf(1.0f / (float)J + 1e-8f);
+        for (int p = 0; p < PPT; ++p) {
+            const float pe = __fdiv_rn(logp[p], osum) + 1e-8f;
+            logp[p] = kFast ? pe : logf(pe);
+        }
+        for (int j = tid; j < Jp; j += NT) S.logq[j] = kFast ? (1.0f / (float)J + 1e-8f) : logf(1.0f / (float)J + 1e-8f);
     } else {
 #pragma unroll
         for (int p = 0; p < PPT; ++p) {
             const int i = tid + p * NT;
-            float pv = P.p ? (i < N ? P.p[(int64_t)b * N + i] : 1.f) : 1.0f / (float)N;
+            const float pv = P.p ? (i < N ? P.p[(int64_t)b * N + i] : 1.f) : 1.0f / (float)N;
             logp[p] = logf(pv + 1e-8f);
             px[p] = py[p] = pz[p] = m2x[p] = m2y[p] = m2z[p] = pn[p] = 0.f;
         }
         for (int j = tid; j < Jp; j += NT) {
-            float qv = P.q ? (j < J ? P.q[(int64_t)b * J + j] : 1.f) : 1.0f / (float)J;
-            s_logq[j] = logf(qv + 1e-8f);
+            const float qv = P.q ? (j < J ? P.q[(int64_t)b * J + j] : 1.f) : 1.0f / (float)J;
+            S.logq[j] = logf(qv + 1e-8f);
         }
     }
     __syncthreads();
 
-    NodeCost ncost{s_node, P.tau == 1.0f ? 1.f : 0.f, P.tau};
+    // Fast path: coordinates are re-read (L1/L2 hits) where they are used instead of being held in registers
+    // across the inner Sinkhorn loop, which needs every register for the G tile.
+    auto reload_xyz = [&]() {
+        if constexpr (kCluster && kFast) {
+            const float* base = P.xyz + (int64_t)b * P.sb;
+#pragma unroll
+            for (int p = 0; p < PPT; ++p) {
+                const int i = tid + p * NT;
+                px[p] = py[p] = pz[p] = 0.f;
+                if (i < N) {
+                    px[p] = base[(int64_t)i * P.sn]; py[p] = base[(int64_t)i * P.sn + P.sc];
+                    pz[p] = base[(int64_t)i * P.sn + 2 * P.sc];
+                }
+                m2x[p] = -2.f * px[p]; m2y[p] = -2.f * py[p]; m2z[p] = -2.f * pz[p];
+                pn[p] = sq3(px[p], py[p], pz[p]);
+            }
+        }
+    };
     const float* cost_b = kCluster ? nullptr : P.cost + (int64_t)b * N * J;
     auto cost_at = [&](int p, int j) -> float {
-        if constexpr (kCluster) return ncost(m2x[p], m2y[p], m2z[p], pn[p], j);
+        if constexpr (kCluster) return node_cost(m2x[p], m2y[p], m2z[p], pn[p], S.node[j], P.tau);
         else return cost_b[(int64_t)(tid + p * NT) * J + j];
     };
 
-    // ---- initial centroids ------------------------------------------------------------------------------
+    // ---- initial centroids ---------------------------------------------------------------------------------
     if constexpr (kCluster) {
-        float* hist_b = P.hist + (int64_t)b * iters * J * 3;
         if (resume == 0) {
             float best[PPT];
-            float sx = 0.f, sy = 0.f, sz = 0.f;
 #pragma unroll
-            for (int p = 0; p < PPT; ++p) { best[p] = 1e10f; if (tid + p * NT < N) { sx += px[p]; sy += py[p]; sz += pz[p]; } }
-            const float cx = block_sum<NT>(sx, s_red) / (float)N;
-            const float cy = block_sum<NT>(sy, s_red) / (float)N;
-            const float cz = block_sum<NT>(sz, s_red) / (float)N;
-            unsigned long long key = 0ull;
-#pragma unroll
-            for (int p = 0; p < PPT; ++p) {
-                const int i = tid + p * NT;
-                if (i < N) {
-                    float dx = px[p] - cx, dy = py[p] - cy, dz = pz[p] - cz;
-                    float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-                    if (d < best[p]) best[p] = d;
-                    unsigned long long k = ((unsigned long long)__float_as_uint(best[p]) << 32) | (0xffffffffu - (unsigned)i);
-                    key = k > key ? k : key;
-                }
-            }
-            key = warp_max_u64(key);
-            __syncthreads();
-            if (lane == 0) s_key[warp] = key;
-            __syncthreads();
-            unsigned long long kk = lane < NW ? s_key[lane] : 0ull;
-            kk = warp_max_u64(kk);
-            int far = (int)(0xffffffffu - (unsigned)(kk & 0xffffffffull));
-            __syncthreads();
-            fps_run<NT, PPT>(px, py, pz, best, N, J, far, s_misc, s_key, [&](int s, int f) {
-                // the owner of point f publishes it as centroid s
-                if ((f % NT) == tid) {
+            for (int p = 0; p < PPT; ++p) best[p] = 1e10f;
+            const int far = fps_center_start<NT, PPT>(px, py, pz, best, N, S.red, S.key);
+            fps_run<NT, PPT>(px, py, pz, best, N, J, far, S.misc, S.key, [&](int s, int f) {
+                if ((f % NT) == tid) {                  // the owner of point f publishes it as centroid s
                     const int slot = f / NT;
 #pragma unroll
                     for (int p = 0; p < PPT; ++p)
-                        if (p == slot) s_node[s] = make_float4(px[p], py[p], pz[p], pn[p]);
+                        if (p == slot) S.node[s] = make_float4(px[p], py[p], pz[p], pn[p]);
                 }
             });
-            __syncthreads();
         } else {
+            const float* h = P.hist + ((int64_t)b * iters + resume) * J * 3;
             for (int j = tid; j < J; j += NT) {
-                const float* h = hist_b + ((int64_t)resume * J + j) * 3;
-                float x = h[0], y = h[1], z = h[2];
-                s_node[j] = make_float4(x, y, z, __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
+                const float x = h[3 * j], y = h[3 * j + 1], z = h[3 * j + 2];
+                S.node[j] = make_float4(x, y, z, sq3(x, y, z));
             }
         }
-        for (int j = J + tid; j < Jp; j += NT) s_node[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = J + tid; j < Jp; j += NT) S.node[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         __syncthreads();
     }
 
-    // ---- outer iterations ------------------------------------------------------------------------------------
+    // ---- outer iterations ----------------------------------------------------------------------------------
     for (int o = resume; o < iters; ++o) {
         if constexpr (kCluster) {
             float* h = P.hist + ((int64_t)b * iters + o) * J * 3;
-            for (int j = tid; j < J; j += NT) { float4 c = s_node[j]; h[3 * j] = c.x; h[3 * j + 1] = c.y; h[3 * j + 2] = c.z; }
+            for (int j = tid; j < J; j += NT) { const float4 c = S.node[j]; h[3 * j] = c.x; h[3 * j + 1] = c.y; h[3 * j + 2] = c.z; }
         }
-        const int n_it = P.launch > 0 ? P.n_inner[o] : max_iter;
-#pragma unroll
-        for (int p = 0; p < PPT; ++p) u[p] = 0.f;
-        for (int j = tid; j < Jp; j += NT) s_v[j] = 0.f;
-        __syncthreads();
+        const int n_it = first ? max_iter : __ldcg(P.n_inner + o);
+        const bool last = (o == iters - 1);
 
-        for (int it = 0; it < n_it; ++it) {
-            // ---- row update: u_i += eps * (log p_i - LSE_j K_ij) ------------------------------------------
-            float du_abs = 0.f;
+        // K_ij of the thread's points after the Sinkhorn call: fast path a_i * G_ij * b_j, else recomputed
+        float G[kFast ? PPT : 1][JF];
+        float a[PPT];
+        bool use_G = false;
+        if constexpr (kFast) {
+            // ---- scaled-domain iterations ------------------------------------------------------------------
+            float mrow[PPT], uold[PPT];
+            reload_xyz();
 #pragma unroll
             for (int p = 0; p < PPT; ++p) {
-                const int i = tid + p * NT;
-                if (i < N) {
-                    float m = -INFINITY, s = 0.f;
-                    for (int j0 = 0; j0 < J; j0 += kJC) {
-                        float x[kJC];
-                        float mc = -INFINITY;
+                float mn = INFINITY;
 #pragma unroll
-                        for (int jj = 0; jj < kJC; ++jj) {
-                            const int j = j0 + jj;
-                            if (j < J) {
-                                x[jj] = __fadd_rn(__fadd_rn(-cost_at(p, j), u[p]), s_v[j]) * k2;
-                                mc = fmaxf(mc, x[jj]);
-                            } else x[jj] = -INFINITY;
-                        }
-                        const float mn = fmaxf(m, mc);
-                        float acc = 0.f;
-#pragma unroll
-                        for (int jj = 0; jj < kJC; ++jj) acc += exp2f(x[jj] - mn);
-                        s = s * exp2f(m - mn) + acc;        // m == -inf on the first chunk -> s*0
-                        m = mn;
-                    }
-                    const float lse = (m + log2f(s)) * kLn2;
-                    const float un = __fadd_rn(__fmul_rn(P.eps, logp[p] - lse), u[p]);
-                    du_abs += fabsf(un - u[p]);
-                    u[p] = un;
+                for (int j = 0; j < JF; ++j) {
+                    G[p][j] = j < J ? node_cost(m2x[p], m2y[p], m2z[p], pn[p], S.node[j], P.tau) : INFINITY;
+                    mn = fminf(mn, G[p][j]);
                 }
-            }
-            // ---- column update: v_j += eps * (log q_j - LSE_i K_ij) -------------------------------------
-            // After the row update every K_ij <= log(p_i + 1e-8) < 0, so the column sums need no
-            // max shift (sum_i exp K_ij <= 1); a column whose sum underflows is redone exactly below.
-            for (int j0 = 0; j0 < J; j0 += kJC) {
-                float part[kJC];
+                mrow[p] = mn;
 #pragma unroll
-                for (int jj = 0; jj < kJC; ++jj) part[jj] = 0.f;
+                for (int j = 0; j < JF; ++j) G[p][j] = (tid + p * NT < N) ? exp2f((mn - G[p][j]) * k2) : 0.f;
+                uold[p] = 0.f;
+                a[p] = 0.f;
+            }
+            if (tid < JF) { S.bq[tid] = tid < J ? 1.f : 0.f; S.v[tid] = 0.f; }
+            if (tid == 0) S.misc[6] = 0.f;
+            __syncthreads();
+            bool tripped = false;
+            for (int it = 0; it < n_it; ++it) {
+                float r[PPT];
+#pragma unroll
+                for (int p = 0; p < PPT; ++p) r[p] = 0.f;
+#pragma unroll
+                for (int j4 = 0; j4 < JF / 4; ++j4) {
+                    const float4 bq = *reinterpret_cast<const float4*>(S.bq + 4 * j4);
+#pragma unroll
+                    for (int p = 0; p < PPT; ++p) {
+                        r[p] = fmaf(G[p][4 * j4 + 0], bq.x, r[p]);
+                        r[p] = fmaf(G[p][4 * j4 + 1], bq.y, r[p]);
+                        r[p] = fmaf(G[p][4 * j4 + 2], bq.z, r[p]);
+                        r[p] = fmaf(G[p][4 * j4 + 3], bq.w, r[p]);
+                    }
+                }
+                float du_abs = 0.f;
 #pragma unroll
                 for (int p = 0; p < PPT; ++p) {
                     if (tid + p * NT < N) {
-#pragma unroll
-                        for (int jj = 0; jj < kJC; ++jj) {
-                            const int j = j0 + jj;
-                            if (j < J) part[jj] += exp2f(__fadd_rn(__fadd_rn(-cost_at(p, j), u[p]), s_v[j]) * k2);
-                        }
+                        a[p] = __fdiv_rn(logp[p], r[p]);
+                        const float un = fmaf(P.eps, __logf(a[p]), mrow[p]);
+                        du_abs += fabsf(un - uold[p]);
+                        uold[p] = un;
                     }
+                }
+                float part[JF];
+#pragma unroll
+                for (int j = 0; j < JF; ++j) {
+                    float acc = 0.f;
+#pragma unroll
+                    for (int p = 0; p < PPT; ++p) acc = fmaf(G[p][j], a[p], acc);
+                    part[j] = acc;
                 }
                 const float tot = butterfly16(part, lane);
-                if ((lane & 1) == 0) s_wtot[warp * Jp + j0 + ((lane >> 1) & 15)] = tot;
-            }
-            du_abs = warp_sum(du_abs);
-            if (lane == 0) s_du[warp] = du_abs;
-            __syncthreads();
-            // final column sums (fixed order over warps) -> staged new v in s_wtot[j] (plane 0, warp-0 row,
-            // which only this thread reads); NaN marks a column that must be redone with a max shift
-            int need_exact = 0;
-            for (int j = tid; j < J; j += NT) {
-                float sj = 0.f;
+                if ((lane & 1) == 0) S.wtot[warp * JF + ((lane >> 1) & 15)] = tot;
+                du_abs = warp_sum(du_abs);
+                if (lane == 0) S.du[warp] = du_abs;
+                __syncthreads();
+                if (warp == 0) {
+                    const int j = lane & 15;
+                    float sj = 0.f;
 #pragma unroll
-                for (int w = 0; w < NW; ++w) sj += s_wtot[w * Jp + j];
-                if (sj > 1e-30f && sj < INFINITY) {
-                    s_wtot[j] = __fadd_rn(__fmul_rn(P.eps, s_logq[j] - logf(sj)), s_v[j]);
-                } else {
-                    s_wtot[j] = NAN;
-                    need_exact = 1;
-                }
-            }
-            if (__syncthreads_or(need_exact)) {
-                // exact max-shifted LSE for the flagged columns (rare: a centroid nobody is near)
-                for (int j = 0; j < J; ++j) {
-                    if (s_wtot[j] == s_wtot[j]) continue;               // block-uniform (shared value)
-                    float mx = -INFINITY;
+                    for (int w = 0; w < NW; ++w) sj += S.wtot[w * JF + j];
+                    const bool live = j < J;
+                    const float bn = live ? __fdiv_rn(S.logq[j], sj) : 0.f;
+                    const float vn = live ? P.eps * __logf(bn) : 0.f;
+                    float dv = (live && lane < 16) ? fabsf(vn - S.v[j]) : 0.f;
+                    bool ok = !live || (sj > 1e-30f && sj < 1e30f);
+                    float bmax = live ? bn : 0.f, bmin = live ? bn : INFINITY;
 #pragma unroll
-                    for (int p = 0; p < PPT; ++p)
-                        if (tid + p * NT < N) mx = fmaxf(mx, __fadd_rn(__fadd_rn(-cost_at(p, j), u[p]), s_v[j]) * k2);
-                    mx = warp_max(mx);
-                    if (lane == 0) s_tmp[warp] = mx;
-                    __syncthreads();
-                    float mall = -INFINITY;
-                    for (int w = 0; w < NW; ++w) mall = fmaxf(mall, s_tmp[w]);
-                    float sm = 0.f;
-#pragma unroll
-                    for (int p = 0; p < PPT; ++p)
-                        if (tid + p * NT < N) sm += exp2f(__fadd_rn(__fadd_rn(-cost_at(p, j), u[p]), s_v[j]) * k2 - mall);
-                    sm = block_sum<NT>(sm, s_red);
-                    if (tid == 0) {
-                        const float lse = (mall + log2f(sm)) * kLn2;
-                        s_wtot[j] = __fadd_rn(__fmul_rn(P.eps, s_logq[j] - lse), s_v[j]);
+                    for (int off = 8; off > 0; off >>= 1) {
+                        dv += __shfl_xor_sync(kFull, dv, off);
+                        bmax = fmaxf(bmax, __shfl_xor_sync(kFull, bmax, off));
+                        bmin = fminf(bmin, __shfl_xor_sync(kFull, bmin, off));
                     }
-                    __syncthreads();
-                }
-            }
-            // commit v, accumulate sum |dv|, record this iteration's change
-            float dv_abs = 0.f;
-            for (int j = tid; j < J; j += NT) {
-                const float vn = s_wtot[j];
-                dv_abs += fabsf(vn - s_v[j]);
-                s_v[j] = vn;
-            }
-            dv_abs = warp_sum(dv_abs);
-            if (lane == 0) s_tmp[warp] = dv_abs;
-            __syncthreads();
-            if (tid == 0) {
-                float du = 0.f, dv = 0.f;
+                    ok = __all_sync(kFull, ok) && (bmax <= bmin * 1e24f);
+                    float du = 0.f;
 #pragma unroll
-                for (int w = 0; w < NW; ++w) { du += s_du[w]; dv += s_tmp[w]; }
-                P.diffs[((int64_t)o * max_iter + it) * P.B + b] = du + dv;
+                    for (int w = 0; w < NW; ++w) du += S.du[w];
+                    if (lane < 16) { S.bq[j] = bn; S.v[j] = vn; }
+                    if (lane == 0) {
+                        P.diffs[((int64_t)o * max_iter + it) * P.B + b] = du + dv;
+                        if (!ok) S.misc[6] = 1.f;
+                    }
+                }
+                __syncthreads();
+                if (S.misc[6] != 0.f) { tripped = true; break; }
             }
-            __syncthreads();
+            use_G = !tripped;
+            if (!tripped) {
+                // fold a_i and b_j into G: K_ij = a_i G_ij b_j
+#pragma unroll
+                for (int j = 0; j < JF; ++j) {
+                    const float bq = S.bq[j];
+#pragma unroll
+                    for (int p = 0; p < PPT; ++p) G[p][j] = a[p] * G[p][j] * bq;
+                }
+            } else {
+                if (tid == 0) atomicAdd(&P.state[2], 1);
+                // rescue: redo this call in the log domain (logp holds p+1e-8 here; the log-domain code wants logs)
+                float lp[PPT];
+                reload_xyz();
+#pragma unroll
+                for (int p = 0; p < PPT; ++p) lp[p] = logf(logp[p]);
+                __syncthreads();
+                for (int j = tid; j < Jp; j += NT) S.logq[j] = logf(S.logq[j]);
+                ld_iterations<NT, PPT>(P, S, b, o, n_it, lp, u, cost_at);
+                for (int j = tid; j < Jp; j += NT) S.logq[j] = 1.0f / (float)J + 1e-8f;
+                __syncthreads();
+            }
+        } else {
+            ld_iterations<NT, PPT>(P, S, b, o, n_it, logp, u, cost_at);
         }
 
-        // ---- gamma = exp(K); nan_to_num; row normalise; M-step on xyz -----------------------------------
-        const bool last = (o == iters - 1);
+        auto k_at = [&](int p, int jj, int j0) -> float {
+            if constexpr (kFast) {
+                if (use_G) return G[p][jj];
+            }
+            const float c = cost_at(p, j0 + jj);
+            return exp2f(__fadd_rn(__fadd_rn(-c, u[p]), S.v[j0 + jj]) * k2);
+        };
+
+        // ---- gamma = exp(K); nan_to_num; row normalise; M-step on xyz ----------------------------------------
         if constexpr (kCluster) {
-            float rinv[PPT];
+            if constexpr (kFast) { if (use_G) reload_xyz(); }
+            float rdiv[PPT];
 #pragma unroll
             for (int p = 0; p < PPT; ++p) {
                 float rs = 0.f;
-                if (tid + p * NT < N)
-                    for (int j = 0; j < J; ++j)
-                        rs += nan_to_num(exp2f(__fadd_rn(__fadd_rn(-cost_at(p, j), u[p]), s_v[j]) * k2), 0.f);
-                rinv[p] = fmaxf(rs, 1e-3f);
+                if (tid + p * NT < N) {
+                    for (int j0 = 0; j0 < J; j0 += kJC)
+#pragma unroll
+                        for (int jj = 0; jj < kJC; ++jj)
+                            if (j0 + jj < J) rs += nan_to_num(k_at(p, jj, j0), 0.f);
+                }
+                rdiv[p] = fmaxf(rs, 1e-3f);
             }
             for (int j0 = 0; j0 < J; j0 += kJC) {
                 float a0[kJC], ax[kJC], ay[kJC], az[kJC];
@@ -469,11 +618,9 @@ sinkhorn_kernel(SinkhornParams P) {
                         float g[kJC];
 #pragma unroll
                         for (int jj = 0; jj < kJC; ++jj) {
-                            const int j = j0 + jj;
                             g[jj] = 0.f;
-                            if (j < J) {
-                                float e = nan_to_num(exp2f(__fadd_rn(__fadd_rn(-cost_at(p, j), u[p]), s_v[j]) * k2), 0.f);
-                                g[jj] = __fdiv_rn(e, rinv[p]);
+                            if (j0 + jj < J) {
+                                g[jj] = __fdiv_rn(nan_to_num(k_at(p, jj, j0), 0.f), rdiv[p]);
                                 a0[jj] += g[jj];
                                 ax[jj] = fmaf(g[jj], px[p], ax[jj]);
                                 ay[jj] = fmaf(g[jj], py[p], ay[jj]);
@@ -482,7 +629,7 @@ sinkhorn_kernel(SinkhornParams P) {
                         }
                         if (last) {
                             float* grow = P.gamma + ((int64_t)b * N + i) * J + j0;
-                            if (((J & 3) == 0)) {
+                            if ((J & 3) == 0) {
 #pragma unroll
                                 for (int jj = 0; jj < kJC; jj += 4)
                                     if (j0 + jj < J)
@@ -501,10 +648,10 @@ sinkhorn_kernel(SinkhornParams P) {
                 const float tz = butterfly16(az, lane);
                 if ((lane & 1) == 0) {
                     const int col = j0 + ((lane >> 1) & 15);
-                    s_wtot[(0 * NW + warp) * Jp + col] = t0;
-                    s_wtot[(1 * NW + warp) * Jp + col] = tx;
-                    s_wtot[(2 * NW + warp) * Jp + col] = ty;
-                    s_wtot[(3 * NW + warp) * Jp + col] = tz;
+                    S.wtot[(0 * NW + warp) * Jp + col] = t0;
+                    S.wtot[(1 * NW + warp) * Jp + col] = tx;
+                    S.wtot[(2 * NW + warp) * Jp + col] = ty;
+                    S.wtot[(3 * NW + warp) * Jp + col] = tz;
                 }
             }
             __syncthreads();
@@ -512,14 +659,14 @@ sinkhorn_kernel(SinkhornParams P) {
                 float s0 = 0.f, sx = 0.f, sy = 0.f, sz = 0.f;
 #pragma unroll
                 for (int w = 0; w < NW; ++w) {
-                    s0 += s_wtot[(0 * NW + w) * Jp + j]; sx += s_wtot[(1 * NW + w) * Jp + j];
-                    sy += s_wtot[(2 * NW + w) * Jp + j]; sz += s_wtot[(3 * NW + w) * Jp + j];
+                    s0 += S.wtot[(0 * NW + w) * Jp + j]; sx += S.wtot[(1 * NW + w) * Jp + j];
+                    sy += S.wtot[(2 * NW + w) * Jp + j]; sz += S.wtot[(3 * NW + w) * Jp + j];
                 }
                 // lib/utils.py:137-140: pi = mean; npi = pi*N + 1e-5; mu = sum / npi
                 const float pi = __fdiv_rn(s0, (float)N);
                 const float npi = __fadd_rn(__fmul_rn(pi, (float)N), 1e-5f);
                 const float mx = __fdiv_rn(sx, npi), my = __fdiv_rn(sy, npi), mz = __fdiv_rn(sz, npi);
-                s_node[j] = make_float4(mx, my, mz, __fadd_rn(__fadd_rn(__fmul_rn(mx, mx), __fmul_rn(my, my)), __fmul_rn(mz, mz)));
+                S.node[j] = make_float4(mx, my, mz, sq3(mx, my, mz));
                 if (last) {
                     P.pi[(int64_t)b * J + j] = pi;
                     float* m = P.mu + ((int64_t)b * J + j) * 3;
@@ -537,32 +684,29 @@ sinkhorn_kernel(SinkhornParams P) {
                     float* grow = P.gamma + ((int64_t)b * N + i) * J;
                     for (int j = 0; j < J; ++j) {
                         const float c = cost_at(p, j);
-                        const float e = exp2f(__fadd_rn(__fadd_rn(-c, u[p]), s_v[j]) * k2);
+                        const float e = exp2f(__fadd_rn(__fadd_rn(-c, u[p]), S.v[j]) * k2);
                         grow[j] = e;
                         lsum = fmaf(e, c, lsum);
                     }
                 }
             }
-            lsum = block_sum<NT>(lsum, s_red);
+            lsum = block_sum<NT>(lsum, S.red);
             if (tid == 0 && P.loss) P.loss[b] = lsum;
             __syncthreads();
         }
     }
+}
 
-    // ---- last CTA: evaluate the batch-mean exit test and publish the schedule ---------------------------
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-        const int prev = atomicAdd(&P.state[1], 1);
-        s_misc[5] = (prev == P.B - 1) ? 1.f : 0.f;
-    }
-    __syncthreads();
-    if (s_misc[5] == 0.f) return;
-    __threadfence();
+// ---- batch-mean exit test: means for (resume.., all inner), then the schedule update (one CTA) ---------------
+template <int NT>
+__device__ __forceinline__ void verify_schedule(const SinkhornParams& P, int resume, bool first) {
+    constexpr int NW = NT / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int iters = P.iters, max_iter = P.max_iter;
     const int total = (iters - resume) * max_iter;
     for (int e = warp; e < total; e += NW) {
         const int o = resume + e / max_iter, it = e % max_iter;
-        const int n_it = P.launch > 0 ? P.n_inner[o] : max_iter;
+        const int n_it = first ? max_iter : P.n_inner[o];
         if (it >= n_it) continue;
         const float* d = P.diffs + ((int64_t)o * max_iter + it) * P.B;
         float acc = 0.f;
@@ -574,19 +718,60 @@ sinkhorn_kernel(SinkhornParams P) {
     if (tid == 0) {
         int new_resume = iters;
         for (int o = resume; o < iters; ++o) {
-            const int n_it = P.launch > 0 ? P.n_inner[o] : max_iter;
+            const int n_it = first ? max_iter : P.n_inner[o];
             int run = n_it;
             for (int it = 0; it < n_it; ++it)
                 if (P.means[o * max_iter + it] < P.thresh) { run = it + 1; break; }
             P.n_inner[o] = run;
             if (run < n_it) { new_resume = o; break; }
         }
-        // outer iterations after a shortened one restart with the full count
-        for (int o = new_resume + 1; o < iters; ++o) P.n_inner[o] = max_iter;
+        for (int o = new_resume + 1; o < iters; ++o) P.n_inner[o] = max_iter;   // restart later calls in full
         if (P.iters_run)
             for (int o = 0; o < iters; ++o) P.iters_run[o] = P.n_inner[o];
         P.state[0] = new_resume;
         P.state[1] = 0;
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// mode 0: main launch, one CTA per cloud, last CTA to finish evaluates the exit test.
+// mode 1: persistent cooperative follow-up; returns at once when the schedule of the main launch stands.
+// (One kernel for both so the cloud body is instantiated once.)
+template <int NT, int PPT, bool kCluster, bool kFast>
+__global__ void __launch_bounds__(NT, (kFast && NT == 256) ? 2 : 1)
+sinkhorn_kernel(SinkhornParams P, int mode) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int resume = 0;
+    if (mode != 0) {
+        resume = __ldcg(P.state);
+        if (resume >= P.iters) return;
+    }
+    namespace cg = cooperative_groups;
+    const int Jp = (P.J + kJC - 1) / kJC * kJC;
+    const Smem S = carve_smem<NT>(smem_raw, Jp);
+    while (resume < P.iters) {
+        for (int b = blockIdx.x; b < P.B; b += gridDim.x) process_cloud<NT, PPT, kCluster, kFast>(P, S, b, resume, mode == 0);
+        __threadfence();
+        if (mode == 0) {
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                const int prev = atomicAdd(&P.state[1], 1);
+                S.misc[5] = (prev == (int)gridDim.x - 1) ? 1.f : 0.f;
+            }
+            __syncthreads();
+            if (S.misc[5] != 0.f) {
+                __threadfence();
+                verify_schedule<NT>(P, 0, true);
+            }
+            return;
+        }
+        cg::grid_group grid = cg::this_grid();
+        grid.sync();
+        if (blockIdx.x == 0) verify_schedule<NT>(P, resume, false);
+        __threadfence();
+        grid.sync();
+        resume = __ldcg(P.state);
     }
 }
 
@@ -608,6 +793,36 @@ using namespace ogmm;
 
 constexpr int64_t kMaxPoints = 8192;
 
+template <int NT, int PPT, bool kCluster, bool kFast>
+static inline int launch_sinkhorn_variant(SinkhornParams P, cudaStream_t s) {
+    const size_t smem = sinkhorn_smem<NT>(P.J);
+    OGMM_REQUIRE(smem <= 200 * 1024, OGMM_EUNSUPPORTED, "sinkhorn: J=%d needs %zu B of shared memory (> 200 KiB)", P.J, smem);
+    auto kern = sinkhorn_kernel<NT, PPT, kCluster, kFast>;
+    int st;
+    if (smem > 48 * 1024) {
+        st = cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(sinkhorn_kernel)");
+        if (st != OGMM_OK) return st;
+    }
+    kern<<<(unsigned)P.B, NT, smem, s>>>(P, 0);
+    st = cuda_status(cudaGetLastError(), "sinkhorn_kernel (main launch)");
+    if (st != OGMM_OK) return st;
+    // co-resident grid for the cooperative follow-up
+    int dev = 0, sms = 0, per_sm = 0;
+    st = cuda_status(cudaGetDevice(&dev), "cudaGetDevice");
+    if (st != OGMM_OK) return st;
+    st = cuda_status(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "cudaDeviceGetAttribute");
+    if (st != OGMM_OK) return st;
+    st = cuda_status(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem), "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+    if (st != OGMM_OK) return st;
+    OGMM_REQUIRE(per_sm >= 1, OGMM_ECUDA, "sinkhorn fix-up kernel does not fit on an SM");
+    int grid = sms * per_sm;
+    if (grid > P.B) grid = P.B;
+    int mode = 1;
+    void* args[] = {&P, &mode};
+    st = cuda_status(cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)grid), dim3(NT), args, smem, s), "sinkhorn_kernel (follow-up launch)");
+    return st;
+}
+
 template <bool kCluster>
 static inline int launch_sinkhorn(SinkhornParams P, void* workspace, int64_t workspace_bytes, ogmm_stream_t stream) {
     const ClusterWsLayout l = cluster_ws_layout(P.B, kCluster ? P.J : 1, P.iters, P.max_iter);
@@ -623,23 +838,15 @@ static inline int launch_sinkhorn(SinkhornParams P, void* workspace, int64_t wor
     cudaStream_t s = as_stream(stream);
     int st = cuda_status(cudaMemsetAsync(ws, 0, 64, s), "cudaMemsetAsync(workspace header)");
     if (st != OGMM_OK) return st;
-    for (int launch = 0; launch <= P.iters; ++launch) {
-        P.launch = launch;
-#define CALL(NT, PPT)                                                                                         \
-    do {                                                                                                      \
-        const size_t smem = sinkhorn_smem<NT>(P.J);                                                           \
-        if (smem > 48 * 1024) {                                                                               \
-            st = cuda_status(cudaFuncSetAttribute(sinkhorn_kernel<NT, PPT, kCluster>,                         \
-                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),    \
-                             "cudaFuncSetAttribute(sinkhorn_kernel)");                                        \
-            if (st != OGMM_OK) return st;                                                                     \
-        }                                                                                                     \
-        sinkhorn_kernel<NT, PPT, kCluster><<<(unsigned)P.B, NT, smem, s>>>(P);                                \
-    } while (0)
-        OGMM_DISPATCH_POINTS(P.N, CALL);
-#undef CALL
-        OGMM_LAUNCH_CHECK("sinkhorn_kernel");
+    if constexpr (kCluster) {
+        if (P.J <= 16 && P.N <= 1024) {
+            if (P.N <= 256) return launch_sinkhorn_variant<256, 1, true, true>(P, s);
+            if (P.N <= 512) return launch_sinkhorn_variant<256, 2, true, true>(P, s);
+            return launch_sinkhorn_variant<256, 4, true, true>(P, s);
+        }
     }
+#define CALL(NT, PPT) return launch_sinkhorn_variant<NT, PPT, kCluster, false>(P, s)
+    OGMM_DISPATCH_POINTS(P.N, CALL);
+#undef CALL
     return OGMM_OK;
 }
-
