@@ -128,133 +128,216 @@ gmm_moments_small_kernel(const float* __restrict__ gamma, int64_t g_sb, int64_t 
 }
 
 // =====================================================================================================
-// wide-feature kernel.  out[j][d] = sum_n gamma[n][j] * f[n][d] / npi[j].
-// CTA = (d tile of TD = 8*DT rows, one cloud).  Each warp owns DT feature rows, each lane an n
-// residue; a thread keeps DT x JP accumulators in registers.  The feature tile [TD][TN] and the gamma
-// tile [TN][JP] are staged through shared memory with coalesced loads; every feature value is read
-// from global memory exactly once, gamma is re-read per d tile (from L2: it was just written).
+// wide-feature kernel.  out[j][d] = sum_n gamma[n][j] * f[n][d] / npi[j]  -- the one HBM-bound kernel.
+//
+// CTA = (tile of TD = 32*DT feature rows, one cloud), 256 threads.  Lane l of every warp owns rows
+// d0 + l + 32 i (i < DT); the 8 warps split the points.  For one point n a thread reads DT feature
+// values (conflict-free: the tile is stored TRANSPOSED, [n][d]) and the 16 responsibilities of that
+// point as four broadcast 128-bit loads, and issues DT*JP/2 packed FFMA2 (fma.rn.f32x2; the feature
+// value is the scalar-broadcast operand) -- ~0.19 shared-memory wavefronts per FMA instruction, so the
+// loop is FP32-pipe bound, not LDS bound.  Features stream HBM -> registers (coalesced LDG.128 along n,
+// L1 no-allocate) -> transposed STS with a row pitch == 2 (mod 8) words (conflict-free stores AND loads),
+// double-buffered: the loads of stage s+1 are in flight while stage s is consumed.  Every feature value
+// is read from HBM exactly once; gamma (64 KB per cloud, just written by the clustering kernel) is
+// re-read from L2 once per feature-row tile.  Partial sums of the 8 warps are folded through shared
+// memory at the end and written coalesced along d.
 // =====================================================================================================
 constexpr int kFeatThreads = 256;
-constexpr int kTN = 128;
-constexpr int kFPad = kTN + 4;
+constexpr int kTN = 32;                              // points per stage
+
+__device__ __forceinline__ void ffma2(float2& d, const float2 a, const float b) {
+    const float2 bb = make_float2(b, b);
+    asm("fma.rn.f32x2 %0, %1, %2, %0;"
+        : "+l"(*reinterpret_cast<unsigned long long*>(&d))
+        : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&bb)));
+}
 
 template <int JP, int DT>
-__global__ void __launch_bounds__(kFeatThreads)
+struct FeatCfg {
+    static constexpr int TD = 32 * DT;
+    static constexpr int PITCH = TD + 2;            // == 2 (mod 8)
+    static constexpr int F_STAGE = kTN * PITCH;     // floats
+    static constexpr int G_STAGE = kTN * JP;
+    static constexpr int RED = (kFeatThreads / 64) * TD * JP;      // fold buffer: half of the warps at a time
+    static constexpr int STAGES_FLOATS = 2 * (F_STAGE + G_STAGE);
+    static constexpr size_t SMEM = sizeof(float) * ((STAGES_FLOATS > RED ? STAGES_FLOATS : RED) + 8 * JP + JP);
+};
+
+template <int JP, int DT>
+__global__ void __launch_bounds__(kFeatThreads, (DT * JP <= 32) ? 3 : ((DT * JP <= 64) ? 2 : 1))
 gmm_moments_feat_kernel(const float* __restrict__ gamma, int64_t g_sb, int64_t g_sn, int64_t g_sj,
                         const float* __restrict__ feats, int64_t f_sb, int64_t f_sn, int64_t f_sd,
                         int N, int J, int D, float* __restrict__ pi_out, float* __restrict__ mu_out) {
-    constexpr int TD = 8 * DT;
-    constexpr int GP = JP + 4;                      // padded gamma row: conflict-free 128-bit reads
+    using C = FeatCfg<JP, DT>;
+    constexpr int TD = C::TD, PITCH = C::PITCH;
     extern __shared__ __align__(16) float sm[];
-    float* s_f = sm;                                // [TD][kFPad]
-    float* s_g = s_f + TD * kFPad;                  // [kTN][GP]
-    float* s_red = s_g + kTN * GP;                  // [8][JP] column sums of gamma per warp
+    float* s_f = sm;                                 // [2][kTN][PITCH]
+    float* s_g = sm + 2 * C::F_STAGE;                // [2][kTN][JP]
+    float* s_red = sm;                               // fold buffer aliases the stages (used after the loop)
+    float* s_gs = sm + (C::STAGES_FLOATS > C::RED ? C::STAGES_FLOATS : C::RED);   // [8][JP] gamma column sums per warp
+    float* s_npi = s_gs + 8 * JP;                    // [JP]
+
     const int b = blockIdx.y, d0 = blockIdx.x * TD;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float* g = gamma + (int64_t)b * g_sb;
     const float* f = feats + (int64_t)b * f_sb;
 
-    float acc[DT][JP];
+    const bool f_fast = (f_sn == 1) && ((f_sd & 3) == 0) && ((f_sb & 3) == 0) && ((reinterpret_cast<uintptr_t>(feats) & 15) == 0) && (d0 + TD <= D);
+    const bool g_fast = (g_sj == 1) && (g_sn == J) && (J == JP) && ((g_sb & 3) == 0) && ((reinterpret_cast<uintptr_t>(gamma) & 15) == 0);
+
+    float2 acc[DT][JP / 2];
 #pragma unroll
     for (int i = 0; i < DT; ++i)
 #pragma unroll
-        for (int j = 0; j < JP; ++j) acc[i][j] = 0.f;
-    float gsum = 0.f;                               // partial sum of gamma column tid % JP
+        for (int j = 0; j < JP / 2; ++j) acc[i][j] = make_float2(0.f, 0.f);
+    constexpr int GC = (JP + 31) / 32;               // gamma columns per lane: j = lane + 32 c
+    float gsum[GC];
+#pragma unroll
+    for (int c = 0; c < GC; ++c) gsum[c] = 0.f;
 
-    const bool f_vec = (f_sn == 1) && ((f_sd & 3) == 0) && ((f_sb & 3) == 0) && ((reinterpret_cast<uintptr_t>(feats) & 15) == 0);
-    const bool g_vec = (g_sj == 1) && (g_sn == J) && ((J & 3) == 0) && ((g_sb & 3) == 0) && ((reinterpret_cast<uintptr_t>(gamma) & 15) == 0);
-
-    for (int n0 = 0; n0 < N; n0 += kTN) {
-        const int tn = min(kTN, N - n0);
-        __syncthreads();
-        // ---- feature tile
-        if (f_vec && tn == kTN) {
-            for (int e = tid; e < TD * (kTN / 4); e += kFeatThreads) {
-                const int r = e / (kTN / 4), c4 = e - r * (kTN / 4);
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (d0 + r < D) v = ldg_stream4(f + (int64_t)(d0 + r) * f_sd + n0 + 4 * c4);
-                *reinterpret_cast<float4*>(s_f + r * kFPad + 4 * c4) = v;
-            }
-        } else if (f_sd == 1) {
-            // (B,N,D) row-major features: sweep d fastest for coalescing
-            for (int e = tid; e < TD * kTN; e += kFeatThreads) {
-                const int c = e / TD, r = e - c * TD;
-                float v = 0.f;
-                if (d0 + r < D && c < tn) v = ldg_stream(f + (int64_t)(n0 + c) * f_sn + (d0 + r));
-                s_f[r * kFPad + c] = v;
-            }
-        } else {
-            for (int e = tid; e < TD * kTN; e += kFeatThreads) {
-                const int r = e / kTN, c = e - r * kTN;
-                float v = 0.f;
-                if (d0 + r < D && c < tn) v = ldg_stream(f + (int64_t)(n0 + c) * f_sn + (int64_t)(d0 + r) * f_sd);
-                s_f[r * kFPad + c] = v;
+    // ---- stage loaders -------------------------------------------------------------------------------
+    // fast path: unit u = tid + 256 k (k < DT) -> 4 consecutive points of one row: c4 = u%4, rsub = (u/4)%8,
+    // block = u/32 -> (row group = block % (TD/8), chunk half = block / (TD/8)).  A warp covers 8 rows x 64 B.
+    float4 fr[DT];
+    constexpr int GQ = (kTN * JP / 4 + kFeatThreads - 1) / kFeatThreads;      // gamma float4s per thread per stage
+    float4 gr[GQ];
+    auto ldg_stage = [&](int n0) {
+        if (f_fast && n0 + kTN <= N) {
+#pragma unroll
+            for (int k = 0; k < DT; ++k) {
+                const int u = tid + kFeatThreads * k;
+                const int c4 = u & 3, rsub = (u >> 2) & 7, blk = u >> 5;
+                const int row = (blk % (TD / 8)) * 8 + rsub, chunk = c4 + 4 * (blk / (TD / 8));
+                fr[k] = ldg_stream4(f + (int64_t)(d0 + row) * f_sd + n0 + 4 * chunk);
             }
         }
-        // ---- gamma tile
-        if (g_vec && tn == kTN && JP == J) {
-            const float4* src = reinterpret_cast<const float4*>(g + (int64_t)n0 * J);
-            for (int e = tid; e < kTN * (JP / 4); e += kFeatThreads) {
-                const int r = e / (JP / 4), c4 = e - r * (JP / 4);
-                *reinterpret_cast<float4*>(s_g + r * GP + 4 * c4) = src[e];
+        if (g_fast && n0 + kTN <= N) {
+#pragma unroll
+            for (int q = 0; q < GQ; ++q)
+                if (tid + kFeatThreads * q < kTN * JP / 4)
+                    gr[q] = *reinterpret_cast<const float4*>(g + (int64_t)n0 * JP + 4 * (tid + kFeatThreads * q));
+        }
+    };
+    auto sts_stage = [&](int n0, int slot) {
+        float* fs = s_f + slot * C::F_STAGE;
+        float* gs = s_g + slot * C::G_STAGE;
+        if (f_fast && n0 + kTN <= N) {
+#pragma unroll
+            for (int k = 0; k < DT; ++k) {
+                const int u = tid + kFeatThreads * k;
+                const int c4 = u & 3, rsub = (u >> 2) & 7, blk = u >> 5;
+                const int row = (blk % (TD / 8)) * 8 + rsub, chunk = c4 + 4 * (blk / (TD / 8));
+                float* dst = fs + (4 * chunk) * PITCH + row;
+                dst[0] = fr[k].x; dst[PITCH] = fr[k].y; dst[2 * PITCH] = fr[k].z; dst[3 * PITCH] = fr[k].w;
             }
+        } else {
+            // generic: any strides, ragged tiles, zero fill
+            const bool d_fastest = (f_sd == 1);
+            for (int e = tid; e < kTN * TD; e += kFeatThreads) {
+                int n, r;
+                if (d_fastest) { n = e / TD; r = e - n * TD; } else { r = e / kTN; n = e - r * kTN; }
+                float v = 0.f;
+                if (n0 + n < N && d0 + r < D) v = ldg_stream(f + (int64_t)(n0 + n) * f_sn + (int64_t)(d0 + r) * f_sd);
+                fs[n * PITCH + r] = v;
+            }
+        }
+        if (g_fast && n0 + kTN <= N) {
+#pragma unroll
+            for (int q = 0; q < GQ; ++q)
+                if (tid + kFeatThreads * q < kTN * JP / 4) *reinterpret_cast<float4*>(gs + 4 * (tid + kFeatThreads * q)) = gr[q];
         } else {
             for (int e = tid; e < kTN * JP; e += kFeatThreads) {
-                const int r = e / JP, c = e - r * JP;
+                const int n = e / JP, j = e - n * JP;
                 float v = 0.f;
-                if (r < tn && c < J) v = g[(int64_t)(n0 + r) * g_sn + (int64_t)c * g_sj];
-                s_g[r * GP + c] = v;
+                if (n0 + n < N && j < J) v = g[(int64_t)(n0 + n) * g_sn + (int64_t)j * g_sj];
+                gs[e] = v;
             }
         }
-        __syncthreads();
-        // ---- gamma column sums (only the d0 == 0 tile publishes pi, but npi is needed by every tile)
-        for (int r = tid / JP; r < kTN; r += kFeatThreads / JP) gsum += s_g[r * GP + (tid % JP)];
-        // ---- accumulate
+    };
+
+    const int n_stages = (N + kTN - 1) / kTN;
+    ldg_stage(0);
+    sts_stage(0, 0);
+    __syncthreads();
+    for (int s = 0; s < n_stages; ++s) {
+        const int slot = s & 1;
+        if (s + 1 < n_stages) ldg_stage((s + 1) * kTN);
+        const float* fs = s_f + slot * C::F_STAGE;
+        const float* gs = s_g + slot * C::G_STAGE;
 #pragma unroll
-        for (int t = 0; t < kTN / 32; ++t) {
-            const int n = lane + 32 * t;
+        for (int t = 0; t < kTN / 8; ++t) {
+            const int n = warp + 8 * t;
             float fv[DT];
 #pragma unroll
-            for (int i = 0; i < DT; ++i) fv[i] = s_f[(warp * DT + i) * kFPad + n];
-            const float4* grow = reinterpret_cast<const float4*>(s_g + n * GP);
+            for (int i = 0; i < DT; ++i) fv[i] = fs[n * PITCH + lane + 32 * i];
 #pragma unroll
-            for (int j4 = 0; j4 < JP / 4; ++j4) {
-                const float4 gv = grow[j4];
+            for (int c = 0; c < GC; ++c)
+                if (lane + 32 * c < JP) gsum[c] += gs[n * JP + lane + 32 * c];
+            const float4* grow = reinterpret_cast<const float4*>(gs + n * JP);
+#pragma unroll
+            for (int q = 0; q < JP / 4; ++q) {
+                const float4 gv = grow[q];
 #pragma unroll
                 for (int i = 0; i < DT; ++i) {
-                    acc[i][4 * j4 + 0] = fmaf(gv.x, fv[i], acc[i][4 * j4 + 0]);
-                    acc[i][4 * j4 + 1] = fmaf(gv.y, fv[i], acc[i][4 * j4 + 1]);
-                    acc[i][4 * j4 + 2] = fmaf(gv.z, fv[i], acc[i][4 * j4 + 2]);
-                    acc[i][4 * j4 + 3] = fmaf(gv.w, fv[i], acc[i][4 * j4 + 3]);
+                    ffma2(acc[i][2 * q], make_float2(gv.x, gv.y), fv[i]);
+                    ffma2(acc[i][2 * q + 1], make_float2(gv.z, gv.w), fv[i]);
                 }
             }
         }
+        if (s + 1 < n_stages) sts_stage((s + 1) * kTN, slot ^ 1);
+        __syncthreads();
     }
-    // ---- reduce gamma column sums: threads with equal tid % JP hold partials of one column
-    __syncthreads();
-    float* s_col = s_g;                              // reuse: [kFeatThreads]
-    s_col[tid] = gsum;
+
+    // ---- gamma column sums -> npi ------------------------------------------------------------------------
+#pragma unroll
+    for (int c = 0; c < GC; ++c)
+        if (lane + 32 * c < JP) s_gs[warp * JP + lane + 32 * c] = gsum[c];
     __syncthreads();
     if (tid < JP) {
         float t = 0.f;
-        for (int r = tid; r < kFeatThreads; r += JP) t += s_col[r];
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += s_gs[w * JP + tid];
         const float pi = __fdiv_rn(t, (float)N);
-        s_red[tid] = __fadd_rn(__fmul_rn(pi, (float)N), 1e-5f);
+        s_npi[tid] = __fadd_rn(__fmul_rn(pi, (float)N), 1e-5f);
         if (blockIdx.x == 0 && tid < J && pi_out) pi_out[(int64_t)b * J + tid] = pi;
     }
-    __syncthreads();
-    // ---- reduce accumulators over the 32 n residues of each warp (16-column butterflies)
+    // ---- fold the 8 warps' partial sums: 4 -> 0..3, then 2,3 -> 0,1, then 1 -> 0 (buffer aliases the stages) --
+    // layout of one warp's block: [j][TD] with d = lane + 32 i contiguous across lanes
+    for (int half = 4; half >= 1; half >>= 1) {
+        __syncthreads();
+        if (warp >= half && warp < 2 * half) {
+            float* dst = s_red + (warp - half) * TD * JP;
 #pragma unroll
-    for (int i = 0; i < DT; ++i) {
-        const int d = d0 + warp * DT + i;
+            for (int i = 0; i < DT; ++i)
 #pragma unroll
-        for (int jc = 0; jc < JP / kJC; ++jc) {
-            float part[kJC];
+                for (int j = 0; j < JP / 2; ++j) {
+                    dst[(2 * j) * TD + lane + 32 * i] = acc[i][j].x;
+                    dst[(2 * j + 1) * TD + lane + 32 * i] = acc[i][j].y;
+                }
+        }
+        __syncthreads();
+        if (warp < half) {
+            const float* src = s_red + warp * TD * JP;
 #pragma unroll
-            for (int jj = 0; jj < kJC; ++jj) part[jj] = acc[i][jc * kJC + jj];
-            const float t = butterfly16(part, lane);
-            const int j = jc * kJC + ((lane >> 1) & 15);
-            if ((lane & 1) == 0 && d < D && j < J) mu_out[((int64_t)b * J + j) * D + d] = __fdiv_rn(t, s_red[j]);
+            for (int i = 0; i < DT; ++i)
+#pragma unroll
+                for (int j = 0; j < JP / 2; ++j) {
+                    acc[i][j].x += src[(2 * j) * TD + lane + 32 * i];
+                    acc[i][j].y += src[(2 * j + 1) * TD + lane + 32 * i];
+                }
+        }
+    }
+    if (warp == 0) {
+#pragma unroll
+        for (int j = 0; j < JP / 2; ++j) {
+#pragma unroll
+            for (int i = 0; i < DT; ++i) {
+                const int d = d0 + lane + 32 * i;
+                if (d < D) {
+                    if (2 * j < J) mu_out[((int64_t)b * J + 2 * j) * D + d] = __fdiv_rn(acc[i][j].x, s_npi[2 * j]);
+                    if (2 * j + 1 < J) mu_out[((int64_t)b * J + 2 * j + 1) * D + d] = __fdiv_rn(acc[i][j].y, s_npi[2 * j + 1]);
+                }
+            }
         }
     }
 }
@@ -352,18 +435,17 @@ extern "C" __attribute__((visibility("default"))) int ogmm_gmm_moments_feat(cons
     cudaStream_t s = as_stream(stream);
 #define LAUNCH(JP, DT)                                                                                              \
     do {                                                                                                            \
-        constexpr int TD = 8 * DT;                                                                                  \
-        const size_t smem = sizeof(float) * ((size_t)TD * kFPad + (size_t)kTN * (JP + 4) + JP + 32);                \
-        if (smem > 48 * 1024) {                                                                                     \
+        using C = FeatCfg<JP, DT>;                                                                                  \
+        if (C::SMEM > 48 * 1024) {                                                                                  \
             int st = cuda_status(cudaFuncSetAttribute(gmm_moments_feat_kernel<JP, DT>,                              \
-                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),      \
+                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM),   \
                                  "cudaFuncSetAttribute(gmm_moments_feat_kernel)");                                  \
             if (st != OGMM_OK) return st;                                                                           \
         }                                                                                                           \
-        dim3 grid((unsigned)((D + TD - 1) / TD), (unsigned)B);                                                      \
-        gmm_moments_feat_kernel<JP, DT><<<grid, kFeatThreads, smem, s>>>(gamma, g_sb, g_sn, g_sj, feats, f_sb,      \
-                                                                         f_sn, f_sd, (int)N, (int)J, (int)D,        \
-                                                                         pi_out, mu_out);                           \
+        dim3 grid((unsigned)((D + C::TD - 1) / C::TD), (unsigned)B);                                                \
+        gmm_moments_feat_kernel<JP, DT><<<grid, kFeatThreads, C::SMEM, s>>>(gamma, g_sb, g_sn, g_sj, feats, f_sb,   \
+                                                                            f_sn, f_sd, (int)N, (int)J, (int)D,     \
+                                                                            pi_out, mu_out);                        \
     } while (0)
     if (J <= 16) LAUNCH(16, 4);
     else if (J <= 32) LAUNCH(32, 2);
