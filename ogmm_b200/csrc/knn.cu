@@ -13,6 +13,8 @@
 // candidates into the register lists together (converged, no per-candidate divergence).  Candidates
 // are visited in index order and every comparison is strict, so equal distances resolve to the LOWEST
 // index -- the documented tie-break (torch.topk's own is unspecified).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace ogmm {
@@ -307,6 +309,11 @@ edge_gather_kernel(const float* __restrict__ x, int64_t sb, int64_t sc, int64_t 
 
 using namespace ogmm;
 
+int ogmm_launch_knn3_sweep(const float* src, int64_t s_sb, int64_t s_sn, int64_t s_sc,
+                           const float* dst, int64_t d_sb, int64_t d_sn, int64_t d_sc,
+                           int64_t B, int64_t N, int64_t M, int64_t k,
+                           int64_t* idx_out, float* dist_out, float* edge_out, cudaStream_t s);
+
 extern "C" __attribute__((visibility("default"))) int ogmm_knn_graph(const float* src, int64_t s_sb, int64_t s_sn, int64_t s_sc,
                               const float* dst, int64_t d_sb, int64_t d_sn, int64_t d_sc,
                               int64_t B, int64_t N, int64_t M, int64_t C, int64_t k, int normalize,
@@ -320,6 +327,14 @@ extern "C" __attribute__((visibility("default"))) int ogmm_knn_graph(const float
     OGMM_REQUIRE(src && dst && idx_out, OGMM_EINVAL, "ogmm_knn_graph: null pointer");
     OGMM_REQUIRE(edge_out == nullptr || (N == M), OGMM_EINVAL, "ogmm_knn_graph: edge_out needs a self graph (N == M)");
     cudaStream_t s = as_stream(stream);
+    // 3-D clouds of up to 4096 points: sorted sweep with slab pruning (knn_sweep.cu); OGMM_KNN_EXHAUSTIVE=1
+    // forces the exhaustive kernel (same results; kept for larger clouds and for A/B timing)
+    if (C == 3 && !normalize && N <= 4096 && M <= 4096) {
+        const char* force = getenv("OGMM_KNN_EXHAUSTIVE");
+        if (!(force && force[0] == '1'))
+            return ogmm_launch_knn3_sweep(src, s_sb, s_sn, s_sc, dst, d_sb, d_sn, d_sc, B, N, M, k, idx_out, dist_out,
+                                          edge_out, s);
+    }
     const bool three = (C == 3);
     dim3 grid((unsigned)((N + (three ? kKnnThreads : kGQ) - 1) / (three ? kKnnThreads : kGQ)), (unsigned)B);
 #define LAUNCH(KK)                                                                                                   \

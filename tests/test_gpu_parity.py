@@ -71,7 +71,7 @@ def test_knn_golden(og, golden):
     assert torch.equal(idc[ok], gc["idx"][ok])
 
 
-@pytest.mark.parametrize("n,m,k", [(1024, 1024, 20), (717, 717, 20), (300, 1500, 5), (64, 40, 1), (33, 33, 33), (2500, 2500, 16)])
+@pytest.mark.parametrize("n,m,k", [(1024, 1024, 20), (717, 717, 20), (300, 1500, 5), (64, 40, 1), (33, 33, 33), (2500, 2500, 16), (4500, 4500, 8), (100, 4200, 20)])
 def test_knn_xyz_sizes(og, n, m, k):
     g = torch.Generator().manual_seed(n * 7 + m)
     src = torch.rand(2, n, 3, generator=g) * 2 - 1
