@@ -19,31 +19,57 @@ STAGES = ("knn_edge", "cluster", "feat_moments", "procrustes")
 
 
 def launches_per_step(iters=10):
-    """Kernel launches of one ``register_hot_path`` call: 2 kNN, 2 x (1 + iters) clustering, 2 feature M-step, 1 head."""
-    return 2 + 2 * (1 + iters) + 2 + 1
+    """Kernel launches of one ``register_hot_path`` call: 2 kNN, 2 x (main + follow-up) clustering, 2 feature M-step, 1 head."""
+    return 2 + 2 * 2 + 2 + 1
+
+
+_side_streams = {}
+
+
+def _side_stream(device):
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=key)
+    return _side_streams[key]
+
+
+def _cloud_chain(x, feats, o, n_clusters, k, iters, timers, tag):
+    """kNN graph + edge features, clustering, feature M-step for one side (src or tgt) on the current stream."""
+    pts = x.transpose(-1, -2)
+    with _Stage(timers, "knn_edge"):
+        edge = ops.knn_graph(pts, pts, k, want_edge=True)[2].permute(0, 3, 1, 2)
+    with _Stage(timers, "cluster"):
+        gam, pi, mu, _ = ops.sinkhorn_cluster(pts, o, n_clusters, iters=iters)
+    with _Stage(timers, "feat_moments"):
+        nf = ops.gmm_moments(gam, feats.transpose(-1, -2))[1]
+    return edge, gam, pi, mu, nf
 
 
 @torch.no_grad()
-def register_hot_path(src, tgt, src_feats, tgt_feats, src_o, tgt_o, n_clusters=16, k=20, iters=10, timers=None):
+def register_hot_path(src, tgt, src_feats, tgt_feats, src_o, tgt_o, n_clusters=16, k=20, iters=10, timers=None,
+                      overlap=True):
     """src, tgt (B,3,N|M); *_feats (B,D,N|M); *_o (B,N|M)  ->  dict with rot (B,3,3), trans (B,3),
     edge_src/edge_tgt (B,6,N,k) views, and the GMM parameters of both clouds.
 
-    ``timers``: optional dict stage -> list of (start_event, end_event) pairs, filled on the current stream.
+    The two clouds of a pair are independent until the registration head, so with ``overlap`` the target
+    chain runs on a side stream next to the source chain (their kernels share the SMs; neither fills the
+    GPU alone at moderate batch sizes).  ``timers``: optional dict stage -> list of (start, end) CUDA events
+    recorded on the stream each stage runs on; pass ``overlap=False`` to time the kernels in isolation.
     """
-    def stage(name):
-        return _Stage(timers, name)
-
-    with stage("knn_edge"):
-        ps, pt = src.transpose(-1, -2), tgt.transpose(-1, -2)
-        edge_s = ops.knn_graph(ps, ps, k, want_edge=True)[2].permute(0, 3, 1, 2)
-        edge_t = ops.knn_graph(pt, pt, k, want_edge=True)[2].permute(0, 3, 1, 2)
-    with stage("cluster"):
-        gam_s, pi_s, mu_s, _ = ops.sinkhorn_cluster(ps, src_o, n_clusters, iters=iters)
-        gam_t, pi_t, mu_t, _ = ops.sinkhorn_cluster(pt, tgt_o, n_clusters, iters=iters)
-    with stage("feat_moments"):
-        nf_s = ops.gmm_moments(gam_s, src_feats.transpose(-1, -2))[1]
-        nf_t = ops.gmm_moments(gam_t, tgt_feats.transpose(-1, -2))[1]
-    with stage("procrustes"):
+    cur = torch.cuda.current_stream(src.device)
+    if overlap:
+        side = _side_stream(src.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            edge_t, gam_t, pi_t, mu_t, nf_t = _cloud_chain(tgt, tgt_feats, tgt_o, n_clusters, k, iters, timers, "tgt")
+        edge_s, gam_s, pi_s, mu_s, nf_s = _cloud_chain(src, src_feats, src_o, n_clusters, k, iters, timers, "src")
+        cur.wait_stream(side)
+        for t in (edge_t, gam_t, pi_t, mu_t, nf_t):
+            t.record_stream(cur)
+    else:
+        edge_s, gam_s, pi_s, mu_s, nf_s = _cloud_chain(src, src_feats, src_o, n_clusters, k, iters, timers, "src")
+        edge_t, gam_t, pi_t, mu_t, nf_t = _cloud_chain(tgt, tgt_feats, tgt_o, n_clusters, k, iters, timers, "tgt")
+    with _Stage(timers, "procrustes"):
         rot, trans, corr, _ = ops.soft_procrustes(mu_s, mu_t, nf_s, nf_t, 0.05)
     return {"rot": rot, "trans": trans, "edge_src": edge_s, "edge_tgt": edge_t, "src_gamma": gam_s, "tgt_gamma": gam_t,
             "src_pi": pi_s, "tgt_pi": pi_t, "src_mu": mu_s, "tgt_mu": mu_t, "src_node_feats": nf_s,
@@ -57,7 +83,7 @@ class _Stage:
     def __enter__(self):
         if self.timers is not None:
             self.start = torch.cuda.Event(enable_timing=True)
-            self.start.record()
+            self.start.record()          # on the current stream of the enclosing ``torch.cuda.stream`` context
 
     def __exit__(self, *exc):
         if self.timers is not None:

@@ -1,0 +1,40 @@
+"""install()/uninstall() against the real reference modules, when the reference checkout is present (authoring
+container only; skipped on the GPU box).  Only name rebinding is checked -- nothing is executed on a GPU."""
+import os
+import sys
+import types
+
+import pytest
+
+REF = "/root/reference"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present")
+def test_install_rebinds_every_import_site_and_uninstall_restores():
+    for name in ("transforms3d", "transforms3d.quaternions", "open3d", "h5py", "plyfile"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["transforms3d"].quaternions = sys.modules["transforms3d.quaternions"]
+    sys.modules["plyfile"].PlyData = getattr(sys.modules["plyfile"], "PlyData", object)
+    sys.modules["plyfile"].PlyElement = getattr(sys.modules["plyfile"], "PlyElement", object)
+    sys.path.insert(0, REF)
+    try:
+        import lib.utils, lib.se3, lib.loss, models.dgcnn, models.attn, models.gmmreg, baseline.deepgmr  # noqa: E401,F401
+        import ogmm_b200 as og
+        from ogmm_b200 import install
+        orig_knn = models.dgcnn.knn
+        orig_wk = models.gmmreg.wkeans_plus
+        done = install.install()
+        assert "models.dgcnn.knn" in done and "models.gmmreg.wkeans_plus" in done and "baseline.deepgmr.gmm_register" in done
+        assert models.dgcnn.knn is og.utils.knn and lib.utils.knn is og.utils.knn
+        assert models.attn.get_graph_feature is og.utils.get_graph_feature
+        assert models.gmmreg.wkeans_plus is og.utils.wkeans_plus and models.gmmreg.GMMSVD is og.modules.GMMSVD
+        assert lib.loss.gmm_params is og.utils.gmm_params and baseline.deepgmr.gmm_register is og.modules.gmm_register
+        assert models.dgcnn.compute_rigid_transformation is og.se3.compute_rigid_transformation
+        # every patched name exists in the reference module it is patched into (no typos in the table)
+        for mod_name, table in install.PATCH_TABLE.items():
+            for attr in table:
+                assert hasattr(sys.modules[mod_name], attr), f"{mod_name}.{attr} does not exist in the reference"
+        install.uninstall()
+        assert models.dgcnn.knn is orig_knn and models.gmmreg.wkeans_plus is orig_wk
+    finally:
+        sys.path.remove(REF)
