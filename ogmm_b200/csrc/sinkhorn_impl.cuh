@@ -61,6 +61,11 @@ __host__ __device__ inline ClusterWsLayout cluster_ws_layout(int64_t B, int64_t 
     return l;
 }
 
+__device__ __forceinline__ float fast_exp2(float x) {         // MUFU.EX2, flush-to-zero: no denormal fix-up code
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ float sq3(float x, float y, float z) {
     return __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
 }
@@ -175,7 +180,7 @@ __device__ __forceinline__ float node_cost(float m2x, float m2y, float m2z, floa
     d2 = __fadd_rn(d2, pn);
     d2 = __fadd_rn(d2, c.w);
     float d;
-    asm("sqrt.approx.f32 %0, %1;" : "=f"(d) : "f"(fmaxf(d2, 0.f)));      // 1 ulp; clamp_min(0).sqrt()
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(d) : "f"(fmaxf(d2, 0.f)));  // 1 ulp; clamp_min(0).sqrt()
     return tau == 1.0f ? d : __fdiv_rn(d, tau);
 }
 
@@ -353,11 +358,11 @@ __device__ __forceinline__ void ld_iterations(const SinkhornParams& P, const Sme
 
 // ---- one cloud, outer iterations resume..iters-1 -----------------------------------------------------------
 // `first`: main launch (every call runs max_iter inner iterations); otherwise counts come from P.n_inner.
-template <int NT, int PPT, bool kCluster, bool kFast>
+template <int NT, int PPT, bool kCluster, bool kFast, bool kExactJ>
 __device__ __forceinline__ void process_cloud(const SinkhornParams& P, const Smem& S, int b, int resume, bool first) {
     constexpr int NW = NT / 32;
     constexpr int JF = 16;                              // fast path register tile width
-    const int N = P.N, J = P.J;
+    const int N = P.N, J = kExactJ ? JF : P.J;                  // kExactJ: J == 16 known at compile time (no column masks)
     const int Jp = kFast ? JF : (J + kJC - 1) / kJC * kJC;      // compile-time in the fast kernel: fixed smem offsets
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int iters = P.iters, max_iter = P.max_iter;
@@ -468,7 +473,6 @@ __device__ __forceinline__ void process_cloud(const SinkhornParams& P, const Sme
         // K_ij of the thread's points after the Sinkhorn call: fast path a_i * G_ij * b_j, else recomputed
         float G[kFast ? PPT : 1][JF];
         float a[PPT];
-        bool use_G = false;
         if constexpr (kFast) {
             // ---- scaled-domain iterations ------------------------------------------------------------------
             float wold[PPT];        // u_old - m_i, where u_i = m_i + eps log a_i
@@ -482,7 +486,7 @@ __device__ __forceinline__ void process_cloud(const SinkhornParams& P, const Sme
                     mn = fminf(mn, G[p][j]);
                 }
 #pragma unroll
-                for (int j = 0; j < JF; ++j) G[p][j] = (tid + p * NT < N) ? exp2f((mn - G[p][j]) * k2) : 0.f;
+                for (int j = 0; j < JF; ++j) G[p][j] = (tid + p * NT < N) ? fast_exp2((mn - G[p][j]) * k2) : 0.f;
                 wold[p] = -mn;          // u_old = 0
                 a[p] = 0.f;
             }
@@ -558,15 +562,100 @@ __device__ __forceinline__ void process_cloud(const SinkhornParams& P, const Sme
                 __syncthreads();
                 if (S.misc[6] != 0.f) { tripped = true; break; }
             }
-            use_G = !tripped;
             if (!tripped) {
-                // fold a_i and b_j into G: K_ij = a_i G_ij b_j
+                // ---- fast post-processing: gamma_ij = K_ij / clip(sum_j K_ij, 1e-3) with K = a G b (finite by the
+                // monitor, so nan_to_num is the identity); M-step sums over t_ij = scale_i G_ij, b_j applied after
+                // the reduction (it is constant along i).
+                reload_xyz();
+                float scale[PPT];
+                {
+                    float rp[PPT];
+#pragma unroll
+                    for (int p = 0; p < PPT; ++p) rp[p] = 0.f;
+#pragma unroll
+                    for (int j4 = 0; j4 < JF / 4; ++j4) {
+                        const float4 bq = *reinterpret_cast<const float4*>(S.bq + 4 * j4);
+#pragma unroll
+                        for (int p = 0; p < PPT; ++p) {
+                            rp[p] = fmaf(G[p][4 * j4 + 0], bq.x, rp[p]);
+                            rp[p] = fmaf(G[p][4 * j4 + 1], bq.y, rp[p]);
+                            rp[p] = fmaf(G[p][4 * j4 + 2], bq.z, rp[p]);
+                            rp[p] = fmaf(G[p][4 * j4 + 3], bq.w, rp[p]);
+                        }
+                    }
+#pragma unroll
+                    for (int p = 0; p < PPT; ++p) scale[p] = a[p] * __frcp_rn(fmaxf(a[p] * rp[p], 1e-3f));
+                }
+                float a0[JF], ax[JF], ay[JF], az[JF];
 #pragma unroll
                 for (int j = 0; j < JF; ++j) {
-                    const float bq = S.bq[j];
+                    float s0 = 0.f, sx = 0.f, sy = 0.f, sz = 0.f;
 #pragma unroll
-                    for (int p = 0; p < PPT; ++p) G[p][j] = a[p] * G[p][j] * bq;
+                    for (int p = 0; p < PPT; ++p) {
+                        const float t = scale[p] * G[p][j];
+                        G[p][j] = t;
+                        s0 += t;
+                        sx = fmaf(t, px[p], sx); sy = fmaf(t, py[p], sy); sz = fmaf(t, pz[p], sz);
+                    }
+                    a0[j] = s0; ax[j] = sx; ay[j] = sy; az[j] = sz;
                 }
+                if (last) {
+#pragma unroll
+                    for (int p = 0; p < PPT; ++p) {
+                        const int i = tid + p * NT;
+                        if (i < N) {
+                            float* grow = P.gamma + ((int64_t)b * N + i) * J;
+                            if (kExactJ || (J & 3) == 0) {
+#pragma unroll
+                                for (int j4 = 0; j4 < JF / 4; ++j4) {
+                                    if (4 * j4 < J) {
+                                        const float4 bq = *reinterpret_cast<const float4*>(S.bq + 4 * j4);
+                                        *reinterpret_cast<float4*>(grow + 4 * j4) = make_float4(
+                                            G[p][4 * j4] * bq.x, G[p][4 * j4 + 1] * bq.y, G[p][4 * j4 + 2] * bq.z, G[p][4 * j4 + 3] * bq.w);
+                                    }
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < JF; ++j)
+                                    if (j < J) grow[j] = G[p][j] * S.bq[j];
+                            }
+                        }
+                    }
+                }
+                const float t0 = butterfly16(a0, lane);
+                const float tx = butterfly16(ax, lane);
+                const float ty = butterfly16(ay, lane);
+                const float tz = butterfly16(az, lane);
+                if ((lane & 1) == 0) {
+                    const int col = (lane >> 1) & 15;
+                    S.wtot[(0 * NW + warp) * JF + col] = t0;
+                    S.wtot[(1 * NW + warp) * JF + col] = tx;
+                    S.wtot[(2 * NW + warp) * JF + col] = ty;
+                    S.wtot[(3 * NW + warp) * JF + col] = tz;
+                }
+                __syncthreads();
+                if (tid < J) {
+                    const int j = tid;
+                    float s0 = 0.f, sx = 0.f, sy = 0.f, sz = 0.f;
+#pragma unroll
+                    for (int w = 0; w < NW; ++w) {
+                        s0 += S.wtot[(0 * NW + w) * JF + j]; sx += S.wtot[(1 * NW + w) * JF + j];
+                        sy += S.wtot[(2 * NW + w) * JF + j]; sz += S.wtot[(3 * NW + w) * JF + j];
+                    }
+                    const float bq = S.bq[j];
+                    s0 *= bq; sx *= bq; sy *= bq; sz *= bq;
+                    const float pi = __fdiv_rn(s0, (float)N);
+                    const float npi = __fadd_rn(__fmul_rn(pi, (float)N), 1e-5f);
+                    const float mx = __fdiv_rn(sx, npi), my = __fdiv_rn(sy, npi), mz = __fdiv_rn(sz, npi);
+                    S.node[j] = make_float4(mx, my, mz, sq3(mx, my, mz));
+                    if (last) {
+                        P.pi[(int64_t)b * J + j] = pi;
+                        float* m = P.mu + ((int64_t)b * J + j) * 3;
+                        m[0] = mx; m[1] = my; m[2] = mz;
+                    }
+                }
+                __syncthreads();
+                continue;           // next outer iteration
             } else {
                 if (tid == 0) atomicAdd(&P.state[2], 1);
                 // rescue: redo this call in the log domain (logp holds p+1e-8 here; the log-domain code wants logs)
@@ -585,17 +674,12 @@ __device__ __forceinline__ void process_cloud(const SinkhornParams& P, const Sme
         }
 
         auto k_at = [&](int p, int jj, int j0) -> float {
-            if constexpr (kFast) {
-                if (use_G) return G[p][jj];
-            }
             const float c = cost_at(p, j0 + jj);
             return exp2f(__fadd_rn(__fadd_rn(-c, u[p]), S.v[j0 + jj]) * k2);
         };
 
         // ---- gamma = exp(K); nan_to_num; row normalise; M-step on xyz ----------------------------------------
         if constexpr (kCluster) {
-            if constexpr (kFast) { if (use_G) reload_xyz(); }
-            // In the scaled path K = a G b is finite by construction (monitor), so nan_to_num is the identity.
             float rinv[PPT];
 #pragma unroll
             for (int p = 0; p < PPT; ++p) {
@@ -604,7 +688,7 @@ __device__ __forceinline__ void process_cloud(const SinkhornParams& P, const Sme
                     for (int j0 = 0; j0 < J; j0 += kJC)
 #pragma unroll
                         for (int jj = 0; jj < kJC; ++jj)
-                            if (j0 + jj < J) rs += use_G ? k_at(p, jj, j0) : nan_to_num(k_at(p, jj, j0), 0.f);
+                            if (j0 + jj < J) rs += nan_to_num(k_at(p, jj, j0), 0.f);
                 }
                 rinv[p] = __frcp_rn(fmaxf(rs, 1e-3f));
             }
@@ -621,8 +705,7 @@ __device__ __forceinline__ void process_cloud(const SinkhornParams& P, const Sme
                         for (int jj = 0; jj < kJC; ++jj) {
                             g[jj] = 0.f;
                             if (j0 + jj < J) {
-                                const float kv = k_at(p, jj, j0);
-                                g[jj] = (use_G ? kv : nan_to_num(kv, 0.f)) * rinv[p];
+                                g[jj] = nan_to_num(k_at(p, jj, j0), 0.f) * rinv[p];
                                 a0[jj] += g[jj];
                                 ax[jj] = fmaf(g[jj], px[p], ax[jj]);
                                 ay[jj] = fmaf(g[jj], py[p], ay[jj]);
@@ -740,7 +823,7 @@ __device__ __forceinline__ void verify_schedule(const SinkhornParams& P, int res
 // mode 0: main launch, one CTA per cloud, last CTA to finish evaluates the exit test.
 // mode 1: persistent cooperative follow-up; returns at once when the schedule of the main launch stands.
 // (One kernel for both so the cloud body is instantiated once.)
-template <int NT, int PPT, bool kCluster, bool kFast>
+template <int NT, int PPT, bool kCluster, bool kFast, bool kExactJ>
 __global__ void __launch_bounds__(NT, (kFast && NT == 256) ? 2 : 1)
 sinkhorn_kernel(SinkhornParams P, int mode) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -753,7 +836,7 @@ sinkhorn_kernel(SinkhornParams P, int mode) {
     const int Jp = kFast ? 16 : (P.J + kJC - 1) / kJC * kJC;
     const Smem S = carve_smem<NT>(smem_raw, Jp);
     while (resume < P.iters) {
-        for (int b = blockIdx.x; b < P.B; b += gridDim.x) process_cloud<NT, PPT, kCluster, kFast>(P, S, b, resume, mode == 0);
+        for (int b = blockIdx.x; b < P.B; b += gridDim.x) process_cloud<NT, PPT, kCluster, kFast, kExactJ>(P, S, b, resume, mode == 0);
         __threadfence();
         if (mode == 0) {
             __syncthreads();
@@ -795,11 +878,11 @@ using namespace ogmm;
 
 constexpr int64_t kMaxPoints = 8192;
 
-template <int NT, int PPT, bool kCluster, bool kFast>
+template <int NT, int PPT, bool kCluster, bool kFast, bool kExactJ = false>
 static inline int launch_sinkhorn_variant(SinkhornParams P, cudaStream_t s) {
     const size_t smem = sinkhorn_smem<NT>(P.J);
     OGMM_REQUIRE(smem <= 200 * 1024, OGMM_EUNSUPPORTED, "sinkhorn: J=%d needs %zu B of shared memory (> 200 KiB)", P.J, smem);
-    auto kern = sinkhorn_kernel<NT, PPT, kCluster, kFast>;
+    auto kern = sinkhorn_kernel<NT, PPT, kCluster, kFast, kExactJ>;
     int st;
     if (smem > 48 * 1024) {
         st = cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(sinkhorn_kernel)");
@@ -844,6 +927,7 @@ static inline int launch_sinkhorn(SinkhornParams P, void* workspace, int64_t wor
         if (P.J <= 16 && P.N <= 1024) {
             if (P.N <= 256) return launch_sinkhorn_variant<256, 1, true, true>(P, s);
             if (P.N <= 512) return launch_sinkhorn_variant<256, 2, true, true>(P, s);
+            if (P.J == 16) return launch_sinkhorn_variant<256, 4, true, true, true>(P, s);
             return launch_sinkhorn_variant<256, 4, true, true>(P, s);
         }
     }
