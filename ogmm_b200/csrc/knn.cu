@@ -314,6 +314,11 @@ int ogmm_launch_knn3_sweep(const float* src, int64_t s_sb, int64_t s_sn, int64_t
                            int64_t B, int64_t N, int64_t M, int64_t k,
                            int64_t* idx_out, float* dist_out, float* edge_out, cudaStream_t s);
 
+int ogmm_launch_knn_wide(const float* src, int64_t s_sb, int64_t s_sn, int64_t s_sc,
+                         const float* dst, int64_t d_sb, int64_t d_sn, int64_t d_sc,
+                         int64_t B, int64_t N, int64_t M, int64_t C, int64_t k, int normalize,
+                         int64_t* idx_out, float* dist_out, int32_t* stats, cudaStream_t s);
+
 extern "C" __attribute__((visibility("default"))) int ogmm_knn_graph(const float* src, int64_t s_sb, int64_t s_sn, int64_t s_sc,
                               const float* dst, int64_t d_sb, int64_t d_sn, int64_t d_sc,
                               int64_t B, int64_t N, int64_t M, int64_t C, int64_t k, int normalize,
@@ -334,6 +339,17 @@ extern "C" __attribute__((visibility("default"))) int ogmm_knn_graph(const float
         if (!(force && force[0] == '1'))
             return ogmm_launch_knn3_sweep(src, s_sb, s_sn, s_sc, dst, d_sb, d_sn, d_sc, B, N, M, k, idx_out, dist_out,
                                           edge_out, s);
+    }
+    // feature-space graphs (32 <= C <= 256, k <= 32): Gram tiles on the tensor cores (knn_wide.cu), exact FP32 re-rank;
+    // OGMM_KNN_NO_TENSOR=1 forces the FP32 FMA kernel (bit-identical results; for A/B checks)
+    if (C >= 32 && C <= 256 && k <= 32) {
+        const char* force = getenv("OGMM_KNN_NO_TENSOR");
+        if (!(force && force[0] == '1')) {
+            int st = ogmm_launch_knn_wide(src, s_sb, s_sn, s_sc, dst, d_sb, d_sn, d_sc, B, N, M, C, k, normalize, idx_out,
+                                          dist_out, nullptr, s);
+            if (st != OGMM_OK || edge_out == nullptr) return st;
+            return ogmm_edge_gather(src, s_sb, s_sc, s_sn, idx_out, B, C, N, k, edge_out, stream);
+        }
     }
     const bool three = (C == 3);
     dim3 grid((unsigned)((N + (three ? kKnnThreads : kGQ) - 1) / (three ? kKnnThreads : kGQ)), (unsigned)B);
@@ -376,4 +392,19 @@ extern "C" __attribute__((visibility("default"))) int ogmm_edge_gather(const flo
                                                                         (int)k, edge_out);
     OGMM_LAUNCH_CHECK("edge_gather_kernel");
     return OGMM_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int ogmm_knn_wide(const float* src, int64_t s_sb, int64_t s_sn, int64_t s_sc,
+                                                                  const float* dst, int64_t d_sb, int64_t d_sn, int64_t d_sc,
+                                                                  int64_t B, int64_t N, int64_t M, int64_t C, int64_t k, int normalize,
+                                                                  int64_t* idx_out, float* dist_out, int32_t* fallback_count,
+                                                                  ogmm_stream_t stream) {
+    OGMM_REQUIRE(B >= 0 && N >= 1 && M >= 1 && k >= 1 && N < (1ll << 31) && M < (1ll << 31) && B < 65536, OGMM_EINVAL,
+                 "ogmm_knn_wide: bad sizes");
+    OGMM_REQUIRE(C >= 32 && C <= 256, OGMM_EUNSUPPORTED, "ogmm_knn_wide: C=%lld outside [32, 256]", (long long)C);
+    OGMM_REQUIRE(k <= M, OGMM_EINVAL, "ogmm_knn_wide: k=%lld exceeds M=%lld", (long long)k, (long long)M);
+    if (B == 0) return OGMM_OK;
+    OGMM_REQUIRE(src && dst && idx_out, OGMM_EINVAL, "ogmm_knn_wide: null pointer");
+    return ogmm_launch_knn_wide(src, s_sb, s_sn, s_sc, dst, d_sb, d_sn, d_sc, B, N, M, C, k, normalize, idx_out, dist_out,
+                                fallback_count, as_stream(stream));
 }

@@ -1,0 +1,402 @@
+// K1w: kNN in feature space (C >= 32) on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.
+//
+// Same contract as the other kNN kernels (lib/utils.py:12-44): the k smallest expanded-form distances
+// ((-2 s.d) + |s|^2) + |d|^2, clamp 1e-12 (or 2 - 2 s.d for normalize), ascending, ties to the lowest index,
+// with the FINAL distances and their order computed in exact FP32 like the reference.  The Gram matrix, which is
+// the only O(N*M*C) part, runs on the tensor cores:
+//
+//   * CTA = 128 queries (MMA M = 128) x all candidates in tiles of BN (MMA N = BN in {256,128,64,32}).  Query and
+//     candidate tiles are staged in shared memory in the canonical K-major SWIZZLE_128B layout (one 128-byte row
+//     = 32 features; software swizzle, chunk ^= row % 8), described to the MMA by shared-memory matrix
+//     descriptors; one elected thread issues C/8 `tcgen05.mma.cta_group::1.kind::tf32` per tile; the FP32
+//     accumulator tile lives in TMEM (BN columns x 128 lanes) and is read back with `tcgen05.ld.32x32b.x32`:
+//     TMEM lane = query = thread, so the selection stays one-thread-per-query.
+//   * TF32 truncates operands to 10 mantissa bits: |dot_tf32 - dot| <= 2^-9 |x||y|.  Exactness is restored in
+//     two passes.  Pass A keeps the K smallest APPROXIMATE distances (values only) -> tau.  Since the K best
+//     approximate candidates have exact distance <= tau + E, every true top-k candidate has approximate distance
+//     <= tau + 2E (E = the per-query error bound).  Pass B recomputes the Gram tiles (the tensor pipe is idle
+//     otherwise) and collects exactly that guaranteed superset (typically k + a handful); the collected
+//     candidates are re-ranked with exact FP32 distances (FMA chain over c, the generic kernel's arithmetic).
+//     If a query's superset overflows its buffer, that query falls back to an exhaustive FP32 scan (exact, slow,
+//     rare), so the result never depends on the tensor-core rounding.
+#include "common.cuh"
+
+namespace ogmm {
+
+constexpr int kWQ = 128;              // queries per CTA (= MMA M = TMEM lanes)
+constexpr int kWThreads = 128;
+constexpr int kWStage = 16;           // staging slots per thread (pass A)
+constexpr int kWTrigger = 8;
+
+typedef unsigned long long u64w;
+// 64-bit list keys: order-preserving image of the float distance (the cosine form can be slightly negative)
+// in the high word, candidate index in the low word -> integer compare == (distance, index) lexicographic order.
+__device__ __forceinline__ unsigned dist_bits(float d) {
+    const unsigned b = __float_as_uint(d + 0.0f);                 // -0 -> +0
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float bits_dist(unsigned k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+constexpr u64w kEmptyKeyW = (0xff800000ull << 32) | 0xffffffffull;   // +inf, largest index
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, int ncols) {      // one full warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+}
+__device__ __forceinline__ void tmem_free(uint32_t taddr, int ncols) {           // same warp as alloc
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols));
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void proxy_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, TF32 inputs, FP32 accumulate; issued by ONE thread.
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {                     // arrives on bar when prior MMAs are done
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Shared-memory matrix descriptor, K-major, SWIZZLE_128B (cute::UMMA::SmemDescriptor): start>>4 | LBO(1)<<16 |
+// SBO(1024 B >> 4)<<32 | version 1 <<46 | layout SWIZZLE_128B(2) <<61.
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3fff) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 (1<<4), A=B=TF32 (2<<7, 2<<10), both K-major,
+// N>>3 at bit 17, M>>4 at bit 24.
+__host__ __device__ inline uint32_t make_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// byte offset of (row, 16-byte chunk) inside one [rows x 128 B] SWIZZLE_128B K-block
+__device__ __forceinline__ uint32_t sw128_off(int row, int chunk) {
+    return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((chunk ^ (row & 7)) << 4));
+}
+
+// ---- lists -----------------------------------------------------------------------------------------------------
+template <int K>
+struct ValList {            // K smallest values (pass A)
+    float d[K];
+    float thr;
+    int cnt;
+    float* sd;
+    int col;
+    __device__ __forceinline__ void init(float* stage, int col_) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) d[j] = INFINITY;
+        thr = INFINITY; cnt = 0; sd = stage; col = col_;
+    }
+    __device__ __forceinline__ void offer(float v) {
+        if (v < thr) { sd[cnt * kWThreads + col] = v; ++cnt; }
+    }
+    __device__ __forceinline__ void insert(float v) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) { const float t = fminf(v, d[j]); v = fmaxf(v, d[j]); d[j] = t; }
+    }
+    __device__ __forceinline__ void merge() {
+        const int most = __reduce_max_sync(kFull, cnt);
+        for (int s = 0; s < most; ++s) {
+            const float v = s < cnt ? sd[s * kWThreads + col] : INFINITY;
+            if (__any_sync(kFull, v < d[K - 1])) insert(v);
+        }
+        cnt = 0;
+        thr = d[K - 1];
+    }
+    __device__ __forceinline__ void maybe_merge() {
+        if (__any_sync(kFull, cnt > kWTrigger)) merge();
+    }
+};
+
+template <int K>
+__device__ __forceinline__ void key_insert(u64w (&key)[K], u64w kv) {
+    if (!(kv < key[K - 1])) return;
+    bool moved = false;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        moved = moved || (kv < key[j]);
+        const u64w t = key[j];
+        key[j] = moved ? kv : t;
+        kv = moved ? t : kv;
+    }
+}
+
+struct WideArgs {
+    const float* src; int64_t s_sb, s_sn, s_sc;
+    const float* dst; int64_t d_sb, d_sn, d_sc;
+    int N, M, C, k, normalize, BN, cap;
+    int64_t* idx_out; float* dist_out; int32_t* stats;     // stats[0] += queries that took the exhaustive fallback
+};
+
+// exact FP32 distance, the generic kernel's arithmetic: fma chain of x_c * (-2 y_c) over c, + |x|^2, + |y|^2, clamp
+__device__ __forceinline__ float exact_dist(const float* __restrict__ x, int64_t x_sc, const float* __restrict__ y, int64_t y_sc,
+                                            int C, float qn, int normalize) {
+    float acc = 0.f, cn = 0.f;
+    for (int c = 0; c < C; ++c) {
+        const float yv = y[(int64_t)c * y_sc];
+        acc = fmaf(x[(int64_t)c * x_sc], -2.f * yv, acc);
+        cn = __fadd_rn(cn, __fmul_rn(yv, yv));
+    }
+    if (normalize) return __fadd_rn(acc, 2.0f);
+    return fmaxf(__fadd_rn(__fadd_rn(acc, qn), cn), 1e-12f);
+}
+
+template <int K>
+__global__ void __launch_bounds__(kWThreads)
+knn_wide_kernel(WideArgs a) {
+    extern __shared__ __align__(16) unsigned char wsm_raw[];
+    // SWIZZLE_128B atoms must sit on 1024-byte boundaries of the shared window: align the carve-up at run time
+    unsigned char* wsm = wsm_raw + ((1024u - (smem_u32(wsm_raw) & 1023u)) & 1023u);
+    const int C = a.C, BN = a.BN, KB = (C + 31) / 32;
+    unsigned char* sA = wsm;                                          // KB x [128 x 128 B]
+    unsigned char* sB = sA + (size_t)KB * kWQ * 128;                  // KB x [BN x 128 B]
+    float* s_cn = reinterpret_cast<float*>(sB + (size_t)KB * BN * 128);   // [BN]
+    float* s_stage = s_cn + BN;                                       // [kWStage][128]
+    int* s_coll = reinterpret_cast<int*>(s_stage + kWStage * kWThreads);  // [cap][128]
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_coll + (size_t)a.cap * kWThreads);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 1);
+
+    const int b = blockIdx.y, q0 = blockIdx.x * kWQ, tid = threadIdx.x, warp = tid >> 5;
+    const float* sb = a.src + (int64_t)b * a.s_sb;
+    const float* db = a.dst + (int64_t)b * a.d_sb;
+    const int q = q0 + tid;
+    const bool valid = q < a.N;
+
+    // ---- one-time setup: barrier, TMEM, query tile ------------------------------------------------------------------
+    if (tid == 0) mbar_init(s_bar, 1);
+    if (warp == 0) tmem_alloc(s_tmem, BN);
+    // query tile -> swizzled K-major smem (zero padded rows / features)
+    const int chunks = KB * 8;                                        // 16-byte chunks per row
+    for (int e = tid; e < kWQ * chunks; e += kWThreads) {
+        const int r = e / chunks, ch = e - r * chunks;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (q0 + r < a.N) {
+            const float* p = sb + (int64_t)(q0 + r) * a.s_sn;
+            const int c = 4 * ch;
+            if (c < C) v.x = p[(int64_t)c * a.s_sc];
+            if (c + 1 < C) v.y = p[(int64_t)(c + 1) * a.s_sc];
+            if (c + 2 < C) v.z = p[(int64_t)(c + 2) * a.s_sc];
+            if (c + 3 < C) v.w = p[(int64_t)(c + 3) * a.s_sc];
+        }
+        *reinterpret_cast<float4*>(sA + (size_t)(ch >> 3) * kWQ * 128 + sw128_off(r, ch & 7)) = v;
+    }
+    float qn = 0.f;
+    if (valid && !a.normalize) {
+        const float* p = sb + (int64_t)q * a.s_sn;
+        for (int c = 0; c < C; ++c) { const float v = p[(int64_t)c * a.s_sc]; qn = __fadd_rn(qn, __fmul_rn(v, v)); }
+    }
+    if (a.normalize) qn = 2.0f;
+    proxy_fence_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+    const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const uint32_t idesc = make_idesc_tf32(kWQ, BN);
+    const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
+    uint32_t parity = 0;
+
+    // loads candidate tile m0 into sB / s_cn and runs the MMAs; on return the accumulators are in TMEM
+    auto gram_tile = [&](int m0) {
+        for (int e = tid; e < BN * chunks; e += kWThreads) {
+            const int r = e / chunks, ch = e - r * chunks;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m0 + r < a.M) {
+                const float* p = db + (int64_t)(m0 + r) * a.d_sn;
+                const int c = 4 * ch;
+                if (c < C) v.x = p[(int64_t)c * a.d_sc];
+                if (c + 1 < C) v.y = p[(int64_t)(c + 1) * a.d_sc];
+                if (c + 2 < C) v.z = p[(int64_t)(c + 2) * a.d_sc];
+                if (c + 3 < C) v.w = p[(int64_t)(c + 3) * a.d_sc];
+            }
+            *reinterpret_cast<float4*>(sB + (size_t)(ch >> 3) * BN * 128 + sw128_off(r, ch & 7)) = v;
+        }
+        for (int r = tid; r < BN; r += kWThreads) {
+            float cn = INFINITY;
+            if (m0 + r < a.M) {
+                cn = 0.f;
+                if (!a.normalize) {
+                    const float* p = db + (int64_t)(m0 + r) * a.d_sn;
+                    for (int c = 0; c < C; ++c) { const float v = p[(int64_t)c * a.d_sc]; cn = __fadd_rn(cn, __fmul_rn(v, v)); }
+                }
+            }
+            s_cn[r] = cn;
+        }
+        proxy_fence_async();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            for (int kb = 0; kb < KB; ++kb) {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const uint64_t da = make_desc_sw128(sA_addr + kb * kWQ * 128 + kk * 32);
+                    const uint64_t dbd = make_desc_sw128(sB_addr + kb * BN * 128 + kk * 32);
+                    umma_tf32(tmem_base, da, dbd, idesc, (kb | kk) ? 1u : 0u);
+                }
+            }
+            umma_commit(s_bar);
+        }
+        mbar_wait(s_bar, parity);
+        parity ^= 1;
+        tc_fence_after();
+    };
+    auto tile_done = [&]() {
+        tc_fence_before();
+        __syncthreads();
+    };
+
+    // ---- pass A: K smallest approximate distances -> tau ---------------------------------------------------------------
+    ValList<K> vl;
+    vl.init(s_stage, tid);
+    float cn_max = 0.f;
+    for (int m0 = 0; m0 < a.M; m0 += BN) {
+        gram_tile(m0);
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            float dot[32];
+            tmem_ld32(tmem_row + c0, dot);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const float cn = s_cn[c0 + i];
+                float v = fmaf(-2.f, dot[i], qn) + cn;
+                if (!a.normalize) v = fmaxf(v, 1e-12f);
+                if (cn < INFINITY) cn_max = fmaxf(cn_max, cn);
+                vl.offer(v);
+                if ((i & 7) == 7) vl.maybe_merge();
+            }
+        }
+        tile_done();
+    }
+    vl.merge();
+    // error bound of the approximate distance: 2 |dot_tf32 - dot| <= 2^-8 |x||y|, plus fp32 rounding slack
+    const float xn = a.normalize ? 1.0f : qn, yn = a.normalize ? 1.0f : cn_max;
+    const float err = 0.00390625f * sqrtf(xn * yn) + 4e-6f * (xn + yn) + 1e-30f;
+    const float thr_b = vl.d[K - 1] + 2.f * err;
+
+    // ---- pass B: collect the guaranteed superset {approx <= tau + 2E} ------------------------------------------------------
+    int ncoll = 0;
+    bool overflow = false;
+    for (int m0 = 0; m0 < a.M; m0 += BN) {
+        gram_tile(m0);
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            float dot[32];
+            tmem_ld32(tmem_row + c0, dot);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                float v = fmaf(-2.f, dot[i], qn) + s_cn[c0 + i];
+                if (!a.normalize) v = fmaxf(v, 1e-12f);
+                if (v <= thr_b && m0 + c0 + i < a.M) {
+                    if (ncoll < a.cap) s_coll[ncoll * kWThreads + tid] = m0 + c0 + i; else overflow = true;
+                    ++ncoll;
+                }
+            }
+        }
+        tile_done();
+    }
+
+    // ---- exact FP32 re-rank (or the exhaustive fallback) -----------------------------------------------------------------------
+    if (valid) {
+        u64w key[K];
+#pragma unroll
+        for (int j = 0; j < K; ++j) key[j] = kEmptyKeyW;
+        const float* x = sb + (int64_t)q * a.s_sn;
+        if (!overflow) {
+            for (int s = 0; s < ncoll; ++s) {
+                const int m = s_coll[s * kWThreads + tid];
+                const float d = exact_dist(x, a.s_sc, db + (int64_t)m * a.d_sn, a.d_sc, C, qn, a.normalize);
+                key_insert<K>(key, ((u64w)dist_bits(d) << 32) | (unsigned)m);
+            }
+        } else {
+            if (a.stats) atomicAdd(a.stats, 1);
+            for (int m = 0; m < a.M; ++m) {
+                const float d = exact_dist(x, a.s_sc, db + (int64_t)m * a.d_sn, a.d_sc, C, qn, a.normalize);
+                key_insert<K>(key, ((u64w)dist_bits(d) << 32) | (unsigned)m);
+            }
+        }
+        int64_t* io = a.idx_out + ((int64_t)b * a.N + q) * a.k;
+        float* dout = a.dist_out ? a.dist_out + ((int64_t)b * a.N + q) * a.k : nullptr;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            if (j < a.k) {
+                io[j] = (int)(unsigned)(key[j] & 0xffffffffull);
+                if (dout) dout[j] = bits_dist((unsigned)(key[j] >> 32));
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 0) tmem_free(tmem_base, BN);
+}
+
+static size_t wide_smem_bytes(int C, int BN, int cap) {
+    const int KB = (C + 31) / 32;
+    return (size_t)KB * kWQ * 128 + (size_t)KB * BN * 128 + 4 * (size_t)BN + 4 * (size_t)kWStage * kWThreads +
+           4 * (size_t)cap * kWThreads + 64 + 1024;
+}
+
+}  // namespace ogmm
+
+using namespace ogmm;
+
+// Called by ogmm_knn_graph / ogmm_knn_wide for 32 <= C <= 256.  `stats` (device int32, may be null) counts the
+// queries that needed the exhaustive fallback.
+int ogmm_launch_knn_wide(const float* src, int64_t s_sb, int64_t s_sn, int64_t s_sc,
+                         const float* dst, int64_t d_sb, int64_t d_sn, int64_t d_sc,
+                         int64_t B, int64_t N, int64_t M, int64_t C, int64_t k, int normalize,
+                         int64_t* idx_out, float* dist_out, int32_t* stats, cudaStream_t s) {
+    OGMM_REQUIRE(k <= 32, OGMM_EUNSUPPORTED, "knn (tensor-core path): k=%lld > 32", (long long)k);
+    // largest candidate tile and superset buffer that fit in shared memory
+    int BN = 256, cap = 64;
+    const size_t limit = 220 * 1024;
+    while (BN > 32 && wide_smem_bytes((int)C, BN, cap) > limit) BN >>= 1;
+    while (cap > 32 && wide_smem_bytes((int)C, BN, cap) > limit) cap -= 16;
+    const size_t smem = wide_smem_bytes((int)C, BN, cap);
+    OGMM_REQUIRE(smem <= limit, OGMM_EUNSUPPORTED, "knn (tensor-core path): C=%lld needs %zu B of shared memory", (long long)C, smem);
+    WideArgs a{src, s_sb, s_sn, s_sc, dst, d_sb, d_sn, d_sc, (int)N, (int)M, (int)C, (int)k, normalize, BN, cap,
+               idx_out, dist_out, stats};
+    dim3 grid((unsigned)((N + kWQ - 1) / kWQ), (unsigned)B);
+#define LAUNCH(KK)                                                                                                   \
+    do {                                                                                                             \
+        int st = cuda_status(cudaFuncSetAttribute(knn_wide_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                                  (int)smem), "cudaFuncSetAttribute(knn_wide_kernel)");              \
+        if (st != OGMM_OK) return st;                                                                                \
+        knn_wide_kernel<KK><<<grid, kWThreads, smem, s>>>(a);                                                        \
+    } while (0)
+    if (k <= 8) LAUNCH(8);
+    else if (k <= 16) LAUNCH(16);
+    else if (k <= 20) LAUNCH(20);
+    else LAUNCH(32);
+#undef LAUNCH
+    OGMM_LAUNCH_CHECK("knn_wide_kernel");
+    return OGMM_OK;
+}

@@ -49,6 +49,22 @@ def knn_graph(src, dst, k, normalize=False, want_edge=False, want_dist=False):
     return idx, dist, edge
 
 
+def knn_wide(src, dst, k, normalize=False, want_dist=False):
+    """Tensor-core feature-space kNN (32 <= C <= 256): idx (B,N,k) int64 [, dist], fallback count (1,) int32."""
+    _need_cuda_f32("src", src); _need_cuda_f32("dst", dst)
+    B, N, C = src.shape
+    M = dst.shape[1]
+    k = int(k)
+    idx = torch.empty((B, N, k), dtype=torch.int64, device=src.device)
+    dist = torch.empty((B, N, k), dtype=torch.float32, device=src.device) if want_dist else None
+    fallback = torch.zeros((1,), dtype=torch.int32, device=src.device)
+    with torch.cuda.device(src.device):
+        st = _lib.load().ogmm_knn_wide(src.data_ptr(), *src.stride(), dst.data_ptr(), *dst.stride(), B, N, M, C, k,
+                                       int(bool(normalize)), idx.data_ptr(), _ptr(dist), fallback.data_ptr(), _stream(src))
+    _lib.check(st, "ogmm_knn_wide")
+    return idx, dist, fallback
+
+
 def edge_gather(x, idx):
     """x (B,C,N) view, idx (B,N,k) int64 -> edge (B,N,k,2C) memory."""
     _need_cuda_f32("x", x)

@@ -18,7 +18,7 @@ def header_symbols():
 
 def test_header_declares_the_documented_entry_points():
     syms = header_symbols()
-    for need in ("ogmm_knn_graph", "ogmm_edge_gather", "ogmm_fps", "ogmm_sinkhorn_cluster", "ogmm_sinkhorn",
+    for need in ("ogmm_knn_graph", "ogmm_knn_wide", "ogmm_edge_gather", "ogmm_fps", "ogmm_sinkhorn_cluster", "ogmm_sinkhorn",
                  "ogmm_gmm_moments", "ogmm_gmm_moments_feat", "ogmm_softmax_moments", "ogmm_rigid_transform",
                  "ogmm_soft_procrustes", "ogmm_cos_similarity", "ogmm_gmm_register", "ogmm_version", "ogmm_last_error"):
         assert need in syms

@@ -107,6 +107,29 @@ def test_knn_strided_views_and_wide(og, golden):
         check_knn(og, f, f, 20)
 
 
+@pytest.mark.parametrize("n,m,c,k,norm", [(1000, 1000, 64, 20, False), (300, 2100, 128, 16, False), (640, 640, 256, 20, False),
+                                          (512, 512, 96, 5, True), (200, 200, 40, 32, False)])
+def test_knn_wide_tensor_core(og, n, m, c, k, norm):
+    """tcgen05 path: identical to the FP32 FMA kernel (same final arithmetic) and to the fp64 order on decidable rows."""
+    import os
+    g = torch.Generator().manual_seed(n + m + c)
+    src = torch.relu(torch.randn(2, n, c, generator=g))
+    dst = src if n == m else torch.relu(torch.randn(2, m, c, generator=g))
+    if norm:
+        src = torch.nn.functional.normalize(src + 0.01, dim=-1)
+        dst = src if n == m else torch.nn.functional.normalize(dst + 0.01, dim=-1)
+    idx, dist, fb = og.ops.knn_wide(cu(src), cu(dst), k, norm, want_dist=True)
+    os.environ["OGMM_KNN_NO_TENSOR"] = "1"
+    try:
+        ref_idx, ref_dist, _ = og.ops.knn_graph(cu(src), cu(dst), k, norm, want_dist=True)
+    finally:
+        del os.environ["OGMM_KNN_NO_TENSOR"]
+    assert torch.equal(idx, ref_idx) and torch.equal(dist, ref_dist), "tensor-core path must equal the FP32 kernel bit for bit"
+    print(f"knn_wide C={c}: exhaustive fallbacks {int(fb)} of {2 * n} queries")
+    assert int(fb) < 0.02 * 2 * n
+    check_knn(og, src, dst, k, norm)          # og.knn routes C >= 32 to the tensor-core kernel
+
+
 def test_edge_features(og, orc, golden):
     g = golden("edge_xyz")
     out = og.get_graph_feature(cu(g["x"]), 8, cu(g["idx"]).clone())
