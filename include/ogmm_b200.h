@@ -66,8 +66,8 @@ int ogmm_knn_graph(const float* src, int64_t s_sb, int64_t s_sn, int64_t s_sc,
  * Same contract as ogmm_knn_graph for 32 <= C <= 256, k <= 32 (ogmm_knn_graph routes such calls here).  The Gram
  * tiles run as tcgen05 TF32 MMAs with TMEM accumulators; a guaranteed superset of the true neighbours is then
  * re-ranked with exact FP32 distances, so idx_out / dist_out are identical to the FP32 kernel's.
- *   fallback_count (optional, device int32, caller-zeroed): incremented once per query whose superset overflowed
- *   its on-chip buffer and was resolved by an exhaustive FP32 scan instead (exact, slow). */
+ *   fallback_count (optional, device int32, caller-zeroed): diagnostic -- incremented once per selector thread whose
+ *   superset buffer filled up and had to be drained early (results are exact either way). */
 int ogmm_knn_wide(const float* src, int64_t s_sb, int64_t s_sn, int64_t s_sc,
                   const float* dst, int64_t d_sb, int64_t d_sn, int64_t d_sc,
                   int64_t B, int64_t N, int64_t M, int64_t C, int64_t k, int normalize,

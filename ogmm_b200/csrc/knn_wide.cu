@@ -17,14 +17,14 @@
 //     <= tau + 2E (E = the per-query error bound).  Pass B recomputes the Gram tiles (the tensor pipe is idle
 //     otherwise) and collects exactly that guaranteed superset (typically k + a handful); the collected
 //     candidates are re-ranked with exact FP32 distances (FMA chain over c, the generic kernel's arithmetic).
-//     If a query's superset overflows its buffer, that query falls back to an exhaustive FP32 scan (exact, slow,
-//     rare), so the result never depends on the tensor-core rounding.
+//     The superset is buffered per selector thread and drained into a sorted exact list whenever the buffer fills,
+//     so its size is unbounded and the result never depends on the tensor-core rounding.
 #include "common.cuh"
 
 namespace ogmm {
 
 constexpr int kWQ = 128;              // queries per CTA (= MMA M = TMEM lanes)
-constexpr int kWThreads = 128;
+constexpr int kWThreads = 256;          // two selector threads per query (they split every tile's columns)
 constexpr int kWStage = 16;           // staging slots per thread (pass A)
 constexpr int kWTrigger = 8;
 
@@ -156,7 +156,7 @@ __device__ __forceinline__ void key_insert(u64w (&key)[K], u64w kv) {
 struct WideArgs {
     const float* src; int64_t s_sb, s_sn, s_sc;
     const float* dst; int64_t d_sb, d_sn, d_sc;
-    int N, M, C, k, normalize, BN, cap;
+    int N, M, C, k, normalize, BN, cap, scratch_words;
     int64_t* idx_out; float* dist_out; int32_t* stats;     // stats[0] += queries that took the exhaustive fallback
 };
 
@@ -173,84 +173,98 @@ __device__ __forceinline__ float exact_dist(const float* __restrict__ x, int64_t
     return fmaxf(__fadd_rn(__fadd_rn(acc, qn), cn), 1e-12f);
 }
 
+// Loads `rows` x C floats (row stride sn, feature stride sc) into the swizzled K-major tile; rows beyond `n_valid`
+// and features beyond C are zero.  128-bit global loads when the features are contiguous and aligned.
+__device__ __forceinline__ void load_tile_sw128(unsigned char* tile, int rows, const float* base, int64_t sn, int64_t sc,
+                                                int row0, int n_valid, int C, int KB, bool vec_ok) {
+    const int chunks = KB * 8;
+    for (int e = threadIdx.x; e < rows * chunks; e += kWThreads) {
+        const int r = e / chunks, ch = e - r * chunks;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int c = 4 * ch;
+        if (row0 + r < n_valid && c < C) {
+            const float* p = base + (int64_t)(row0 + r) * sn;
+            if (vec_ok && c + 3 < C) v = *reinterpret_cast<const float4*>(p + c);
+            else {
+                v.x = p[(int64_t)c * sc];
+                if (c + 1 < C) v.y = p[(int64_t)(c + 1) * sc];
+                if (c + 2 < C) v.z = p[(int64_t)(c + 2) * sc];
+                if (c + 3 < C) v.w = p[(int64_t)(c + 3) * sc];
+            }
+        }
+        *reinterpret_cast<float4*>(tile + (size_t)(ch >> 3) * rows * 128 + sw128_off(r, ch & 7)) = v;
+    }
+}
+
+// |row|^2 of one tile row read back from the swizzled tile, sequential over c with separately rounded products
+// (torch.sum(x ** 2, -1) order, the generic kernel's arithmetic).
+__device__ __forceinline__ float row_sqnorm_sw128(const unsigned char* tile, int rows, int r, int C) {
+    float acc = 0.f;
+    for (int ch = 0; 4 * ch < C; ++ch) {
+        const float4 v = *reinterpret_cast<const float4*>(tile + (size_t)(ch >> 3) * rows * 128 + sw128_off(r, ch & 7));
+        acc = __fadd_rn(acc, __fmul_rn(v.x, v.x));
+        if (4 * ch + 1 < C) acc = __fadd_rn(acc, __fmul_rn(v.y, v.y));
+        if (4 * ch + 2 < C) acc = __fadd_rn(acc, __fmul_rn(v.z, v.z));
+        if (4 * ch + 3 < C) acc = __fadd_rn(acc, __fmul_rn(v.w, v.w));
+    }
+    return acc;
+}
+
+// CTA = 256 threads = 8 warps.  Thread t serves query (t & 127); warps w and w+4 share TMEM lane quadrant w & 3 and
+// split the columns of every tile (half = t >> 7), so each query has two selector threads.
 template <int K>
-__global__ void __launch_bounds__(kWThreads)
+__global__ void __launch_bounds__(kWThreads, 2)
 knn_wide_kernel(WideArgs a) {
     extern __shared__ __align__(16) unsigned char wsm_raw[];
     // SWIZZLE_128B atoms must sit on 1024-byte boundaries of the shared window: align the carve-up at run time
     unsigned char* wsm = wsm_raw + ((1024u - (smem_u32(wsm_raw) & 1023u)) & 1023u);
-    const int C = a.C, BN = a.BN, KB = (C + 31) / 32;
+    const int C = a.C, BN = a.BN, KB = (C + 31) / 32, cap2 = a.cap / 2;
     unsigned char* sA = wsm;                                          // KB x [128 x 128 B]
     unsigned char* sB = sA + (size_t)KB * kWQ * 128;                  // KB x [BN x 128 B]
     float* s_cn = reinterpret_cast<float*>(sB + (size_t)KB * BN * 128);   // [BN]
-    float* s_stage = s_cn + BN;                                       // [kWStage][128]
-    int* s_coll = reinterpret_cast<int*>(s_stage + kWStage * kWThreads);  // [cap][128]
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_coll + (size_t)a.cap * kWThreads);
+    // one scratch region, three consecutive uses: pass-A staging [kWStage][256], the two K-lists per query
+    // [K][256] right after pass A, and the pass-B superset buffer [cap][128]
+    float* s_stage = s_cn + BN;
+    int* s_coll = reinterpret_cast<int*>(s_stage);
+    int* s_cnt = s_coll + a.scratch_words;                            // [256]
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_cnt + kWThreads);
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 1);
+    int* s_cnmax = reinterpret_cast<int*>(s_tmem + 1);
 
     const int b = blockIdx.y, q0 = blockIdx.x * kWQ, tid = threadIdx.x, warp = tid >> 5;
+    const int ql = tid & (kWQ - 1), half = tid >> 7;
     const float* sb = a.src + (int64_t)b * a.s_sb;
     const float* db = a.dst + (int64_t)b * a.d_sb;
-    const int q = q0 + tid;
+    const int q = q0 + ql;
     const bool valid = q < a.N;
+    const bool s_vec = (a.s_sc == 1) && ((a.s_sn & 3) == 0) && ((a.s_sb & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.src) & 15) == 0);
+    const bool d_vec = (a.d_sc == 1) && ((a.d_sn & 3) == 0) && ((a.d_sb & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.dst) & 15) == 0);
 
     // ---- one-time setup: barrier, TMEM, query tile ------------------------------------------------------------------
-    if (tid == 0) mbar_init(s_bar, 1);
+    if (tid == 0) { mbar_init(s_bar, 1); *s_cnmax = 0; }
     if (warp == 0) tmem_alloc(s_tmem, BN);
-    // query tile -> swizzled K-major smem (zero padded rows / features)
-    const int chunks = KB * 8;                                        // 16-byte chunks per row
-    for (int e = tid; e < kWQ * chunks; e += kWThreads) {
-        const int r = e / chunks, ch = e - r * chunks;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (q0 + r < a.N) {
-            const float* p = sb + (int64_t)(q0 + r) * a.s_sn;
-            const int c = 4 * ch;
-            if (c < C) v.x = p[(int64_t)c * a.s_sc];
-            if (c + 1 < C) v.y = p[(int64_t)(c + 1) * a.s_sc];
-            if (c + 2 < C) v.z = p[(int64_t)(c + 2) * a.s_sc];
-            if (c + 3 < C) v.w = p[(int64_t)(c + 3) * a.s_sc];
-        }
-        *reinterpret_cast<float4*>(sA + (size_t)(ch >> 3) * kWQ * 128 + sw128_off(r, ch & 7)) = v;
-    }
-    float qn = 0.f;
-    if (valid && !a.normalize) {
-        const float* p = sb + (int64_t)q * a.s_sn;
-        for (int c = 0; c < C; ++c) { const float v = p[(int64_t)c * a.s_sc]; qn = __fadd_rn(qn, __fmul_rn(v, v)); }
-    }
-    if (a.normalize) qn = 2.0f;
+    load_tile_sw128(sA, kWQ, sb, a.s_sn, a.s_sc, q0, a.N, C, KB, s_vec);
     proxy_fence_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    const float qn = a.normalize ? 2.0f : row_sqnorm_sw128(sA, kWQ, ql, C);
     const uint32_t tmem_base = *s_tmem;
-    const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const uint32_t tmem_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t idesc = make_idesc_tf32(kWQ, BN);
     const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
     uint32_t parity = 0;
+    const int col_lo = half * (BN / 2), col_hi = col_lo + BN / 2;
 
     // loads candidate tile m0 into sB / s_cn and runs the MMAs; on return the accumulators are in TMEM
-    auto gram_tile = [&](int m0) {
-        for (int e = tid; e < BN * chunks; e += kWThreads) {
-            const int r = e / chunks, ch = e - r * chunks;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (m0 + r < a.M) {
-                const float* p = db + (int64_t)(m0 + r) * a.d_sn;
-                const int c = 4 * ch;
-                if (c < C) v.x = p[(int64_t)c * a.d_sc];
-                if (c + 1 < C) v.y = p[(int64_t)(c + 1) * a.d_sc];
-                if (c + 2 < C) v.z = p[(int64_t)(c + 2) * a.d_sc];
-                if (c + 3 < C) v.w = p[(int64_t)(c + 3) * a.d_sc];
-            }
-            *reinterpret_cast<float4*>(sB + (size_t)(ch >> 3) * BN * 128 + sw128_off(r, ch & 7)) = v;
-        }
+    auto gram_tile = [&](int m0, bool track_max) {
+        load_tile_sw128(sB, BN, db, a.d_sn, a.d_sc, m0, a.M, C, KB, d_vec);
+        __syncthreads();
         for (int r = tid; r < BN; r += kWThreads) {
             float cn = INFINITY;
             if (m0 + r < a.M) {
-                cn = 0.f;
-                if (!a.normalize) {
-                    const float* p = db + (int64_t)(m0 + r) * a.d_sn;
-                    for (int c = 0; c < C; ++c) { const float v = p[(int64_t)c * a.d_sc]; cn = __fadd_rn(cn, __fmul_rn(v, v)); }
-                }
+                cn = a.normalize ? 0.f : row_sqnorm_sw128(sB, BN, r, C);
+                if (track_max) atomicMax(s_cnmax, __float_as_int(cn));
             }
             s_cn[r] = cn;
         }
@@ -277,21 +291,18 @@ knn_wide_kernel(WideArgs a) {
         __syncthreads();
     };
 
-    // ---- pass A: K smallest approximate distances -> tau ---------------------------------------------------------------
+    // ---- pass A: K smallest approximate distances of this thread's column halves ---------------------------------------
     ValList<K> vl;
     vl.init(s_stage, tid);
-    float cn_max = 0.f;
     for (int m0 = 0; m0 < a.M; m0 += BN) {
-        gram_tile(m0);
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        gram_tile(m0, true);
+        for (int c0 = col_lo; c0 < col_hi; c0 += 32) {
             float dot[32];
             tmem_ld32(tmem_row + c0, dot);
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-                const float cn = s_cn[c0 + i];
-                float v = fmaf(-2.f, dot[i], qn) + cn;
+                float v = fmaf(-2.f, dot[i], qn) + s_cn[c0 + i];
                 if (!a.normalize) v = fmaxf(v, 1e-12f);
-                if (cn < INFINITY) cn_max = fmaxf(cn_max, cn);
                 vl.offer(v);
                 if ((i & 7) == 7) vl.maybe_merge();
             }
@@ -299,51 +310,76 @@ knn_wide_kernel(WideArgs a) {
         tile_done();
     }
     vl.merge();
+    __syncthreads();                                                    // staging (same scratch) is dead from here
+    // tau = K-th smallest of the union of the two halves' lists (both threads of a query compute it)
+    float* s_lists = reinterpret_cast<float*>(s_coll);                 // [K][256]
+#pragma unroll
+    for (int j = 0; j < K; ++j) s_lists[j * kWThreads + tid] = vl.d[j];
+    __syncthreads();
+    float tau;
+    {
+        const int t0 = ql, t1 = ql + kWQ;
+        int i0 = 0, i1 = 0;
+        tau = INFINITY;
+        for (int t = 0; t < K; ++t) {
+            const float x0 = s_lists[i0 * kWThreads + t0], x1 = s_lists[i1 * kWThreads + t1];
+            if (x0 <= x1) { tau = x0; ++i0; } else { tau = x1; ++i1; }
+        }
+    }
+    const float cn_max = __int_as_float(*s_cnmax);
+    __syncthreads();                                                    // s_lists (= s_coll) is reused below
     // error bound of the approximate distance: 2 |dot_tf32 - dot| <= 2^-8 |x||y|, plus fp32 rounding slack
     const float xn = a.normalize ? 1.0f : qn, yn = a.normalize ? 1.0f : cn_max;
     const float err = 0.00390625f * sqrtf(xn * yn) + 4e-6f * (xn + yn) + 1e-30f;
-    const float thr_b = vl.d[K - 1] + 2.f * err;
+    const float thr_b = tau + 2.f * err;
 
-    // ---- pass B: collect the guaranteed superset {approx <= tau + 2E} ------------------------------------------------------
-    int ncoll = 0;
-    bool overflow = false;
+    // ---- pass B: collect the guaranteed superset {approx <= tau + 2E}; exact FP32 re-rank -------------------------------------
+    // Each selector thread buffers candidate indices in its slice of the scratch region and re-ranks them with exact
+    // distances into its own sorted key list when the slice fills up (rare) and once at the end (converged), so the
+    // buffer size never limits correctness.
+    u64w key[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) key[j] = kEmptyKeyW;
+    const float* x = sb + (int64_t)(valid ? q : 0) * a.s_sn;
+    int ncoll = 0, drains = 0;
+    auto drain = [&]() {
+        for (int s = 0; s < ncoll; ++s) {
+            const int m = s_coll[(half * cap2 + s) * kWQ + ql];
+            const float d = exact_dist(x, a.s_sc, db + (int64_t)m * a.d_sn, a.d_sc, C, qn, a.normalize);
+            key_insert<K>(key, ((u64w)dist_bits(d) << 32) | (unsigned)m);
+        }
+        ncoll = 0;
+    };
     for (int m0 = 0; m0 < a.M; m0 += BN) {
-        gram_tile(m0);
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        gram_tile(m0, false);
+        for (int c0 = col_lo; c0 < col_hi; c0 += 32) {
             float dot[32];
             tmem_ld32(tmem_row + c0, dot);
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
                 float v = fmaf(-2.f, dot[i], qn) + s_cn[c0 + i];
                 if (!a.normalize) v = fmaxf(v, 1e-12f);
-                if (v <= thr_b && m0 + c0 + i < a.M) {
-                    if (ncoll < a.cap) s_coll[ncoll * kWThreads + tid] = m0 + c0 + i; else overflow = true;
-                    ++ncoll;
+                if (v <= thr_b && m0 + c0 + i < a.M && valid) {
+                    s_coll[(half * cap2 + ncoll) * kWQ + ql] = m0 + c0 + i;
+                    if (++ncoll == cap2) { drain(); ++drains; }
                 }
             }
         }
         tile_done();
     }
-
-    // ---- exact FP32 re-rank (or the exhaustive fallback) -----------------------------------------------------------------------
-    if (valid) {
-        u64w key[K];
+    drain();
+    if (drains > 0 && a.stats) atomicAdd(a.stats, 1);
+    __syncthreads();                                                    // superset buffer is dead: reuse for the hand-over
+    // the second selector of each query hands its list to the first one
+    u64w* s_keys = reinterpret_cast<u64w*>(s_coll);                    // [K][128]
+    if (half == 1) {
 #pragma unroll
-        for (int j = 0; j < K; ++j) key[j] = kEmptyKeyW;
-        const float* x = sb + (int64_t)q * a.s_sn;
-        if (!overflow) {
-            for (int s = 0; s < ncoll; ++s) {
-                const int m = s_coll[s * kWThreads + tid];
-                const float d = exact_dist(x, a.s_sc, db + (int64_t)m * a.d_sn, a.d_sc, C, qn, a.normalize);
-                key_insert<K>(key, ((u64w)dist_bits(d) << 32) | (unsigned)m);
-            }
-        } else {
-            if (a.stats) atomicAdd(a.stats, 1);
-            for (int m = 0; m < a.M; ++m) {
-                const float d = exact_dist(x, a.s_sc, db + (int64_t)m * a.d_sn, a.d_sc, C, qn, a.normalize);
-                key_insert<K>(key, ((u64w)dist_bits(d) << 32) | (unsigned)m);
-            }
-        }
+        for (int j = 0; j < K; ++j) s_keys[j * kWQ + ql] = key[j];
+    }
+    __syncthreads();
+    if (valid && half == 0) {
+#pragma unroll 1
+        for (int j = 0; j < K; ++j) key_insert<K>(key, s_keys[j * kWQ + ql]);
         int64_t* io = a.idx_out + ((int64_t)b * a.N + q) * a.k;
         float* dout = a.dist_out ? a.dist_out + ((int64_t)b * a.N + q) * a.k : nullptr;
 #pragma unroll
@@ -358,10 +394,16 @@ knn_wide_kernel(WideArgs a) {
     if (warp == 0) tmem_free(tmem_base, BN);
 }
 
-static size_t wide_smem_bytes(int C, int BN, int cap) {
+static int wide_scratch_words(int cap, int K) {
+    int w = kWStage * kWThreads;                      // staging
+    if (cap * kWQ > w) w = cap * kWQ;                 // superset buffer
+    if (K * kWThreads > w) w = K * kWThreads;         // K-lists after pass A; key hand-over after pass B ([K][128] u64)
+    return w;
+}
+static size_t wide_smem_bytes(int C, int BN, int cap, int K) {
     const int KB = (C + 31) / 32;
-    return (size_t)KB * kWQ * 128 + (size_t)KB * BN * 128 + 4 * (size_t)BN + 4 * (size_t)kWStage * kWThreads +
-           4 * (size_t)cap * kWThreads + 64 + 1024;
+    return (size_t)KB * kWQ * 128 + (size_t)KB * BN * 128 + 4 * (size_t)BN + 4 * (size_t)wide_scratch_words(cap, K) +
+           4 * (size_t)kWThreads + 64 + 1024;
 }
 
 }  // namespace ogmm
@@ -375,15 +417,21 @@ int ogmm_launch_knn_wide(const float* src, int64_t s_sb, int64_t s_sn, int64_t s
                          int64_t B, int64_t N, int64_t M, int64_t C, int64_t k, int normalize,
                          int64_t* idx_out, float* dist_out, int32_t* stats, cudaStream_t s) {
     OGMM_REQUIRE(k <= 32, OGMM_EUNSUPPORTED, "knn (tensor-core path): k=%lld > 32", (long long)k);
-    // largest candidate tile and superset buffer that fit in shared memory
-    int BN = 256, cap = 64;
-    const size_t limit = 220 * 1024;
-    while (BN > 32 && wide_smem_bytes((int)C, BN, cap) > limit) BN >>= 1;
-    while (cap > 32 && wide_smem_bytes((int)C, BN, cap) > limit) cap -= 16;
-    const size_t smem = wide_smem_bytes((int)C, BN, cap);
-    OGMM_REQUIRE(smem <= limit, OGMM_EUNSUPPORTED, "knn (tensor-core path): C=%lld needs %zu B of shared memory", (long long)C, smem);
+    // candidate tile and superset buffer: two CTAs per SM when they fit (selection is latency bound, it wants warps),
+    // else the largest tile that fits one CTA
+    const int K = k <= 8 ? 8 : (k <= 16 ? 16 : (k <= 20 ? 20 : 32));
+    int BN = 128, cap = 64;
+    const size_t limit = 226 * 1024, half_limit = 112 * 1024;
+    if (wide_smem_bytes((int)C, BN, cap, K) > half_limit) {
+        BN = 256;
+        while (BN > 64 && wide_smem_bytes((int)C, BN, cap, K) > limit) BN >>= 1;
+        while (cap > 32 && wide_smem_bytes((int)C, BN, cap, K) > limit) cap -= 8;
+    }
+    const size_t smem = wide_smem_bytes((int)C, BN, cap, K);
+    OGMM_REQUIRE(smem <= limit, OGMM_EUNSUPPORTED, "knn (tensor-core path): C=%lld k=%lld needs %zu B of shared memory",
+                 (long long)C, (long long)k, smem);
     WideArgs a{src, s_sb, s_sn, s_sc, dst, d_sb, d_sn, d_sc, (int)N, (int)M, (int)C, (int)k, normalize, BN, cap,
-               idx_out, dist_out, stats};
+               wide_scratch_words(cap, K), idx_out, dist_out, stats};
     dim3 grid((unsigned)((N + kWQ - 1) / kWQ), (unsigned)B);
 #define LAUNCH(KK)                                                                                                   \
     do {                                                                                                             \
