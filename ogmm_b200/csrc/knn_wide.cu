@@ -178,8 +178,11 @@ __device__ __forceinline__ float exact_dist(const float* __restrict__ x, int64_t
 __device__ __forceinline__ void load_tile_sw128(unsigned char* tile, int rows, const float* base, int64_t sn, int64_t sc,
                                                 int row0, int n_valid, int C, int KB, bool vec_ok) {
     const int chunks = KB * 8;
+    const int sh = 31 - __clz(chunks);
+    const bool pow2 = (chunks & (chunks - 1)) == 0;
     for (int e = threadIdx.x; e < rows * chunks; e += kWThreads) {
-        const int r = e / chunks, ch = e - r * chunks;
+        const int r = pow2 ? (e >> sh) : e / chunks;
+        const int ch = e - r * chunks;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         const int c = 4 * ch;
         if (row0 + r < n_valid && c < C) {
@@ -254,6 +257,7 @@ knn_wide_kernel(WideArgs a) {
     const uint32_t idesc = make_idesc_tf32(kWQ, BN);
     const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
     uint32_t parity = 0;
+    const float floor_d = a.normalize ? -INFINITY : 1e-12f;           // clamp(min=1e-12) of the non-cosine form
     const int col_lo = half * (BN / 2), col_hi = col_lo + BN / 2;
 
     // loads candidate tile m0 into sB / s_cn and runs the MMAs; on return the accumulators are in TMEM
@@ -300,11 +304,16 @@ knn_wide_kernel(WideArgs a) {
             float dot[32];
             tmem_ld32(tmem_row + c0, dot);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                float v = fmaf(-2.f, dot[i], qn) + s_cn[c0 + i];
-                if (!a.normalize) v = fmaxf(v, 1e-12f);
-                vl.offer(v);
-                if ((i & 7) == 7) vl.maybe_merge();
+            for (int i4 = 0; i4 < 8; ++i4) {
+                const float4 cn4 = *reinterpret_cast<const float4*>(s_cn + c0 + 4 * i4);
+                const float cnv[4] = {cn4.x, cn4.y, cn4.z, cn4.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    float v = fmaf(-2.f, dot[4 * i4 + u], qn) + cnv[u];
+                    v = fmaxf(v, floor_d);
+                    vl.offer(v);
+                }
+                if (i4 & 1) vl.maybe_merge();
             }
         }
         tile_done();
@@ -331,7 +340,8 @@ knn_wide_kernel(WideArgs a) {
     // error bound of the approximate distance: 2 |dot_tf32 - dot| <= 2^-8 |x||y|, plus fp32 rounding slack
     const float xn = a.normalize ? 1.0f : qn, yn = a.normalize ? 1.0f : cn_max;
     const float err = 0.00390625f * sqrtf(xn * yn) + 4e-6f * (xn + yn) + 1e-30f;
-    const float thr_b = tau + 2.f * err;
+    // finite even when fewer than K candidates exist, and -inf for padding query rows: they never collect
+    const float thr_b = valid ? fminf(tau + 2.f * err, 3.0e38f) : -INFINITY;
 
     // ---- pass B: collect the guaranteed superset {approx <= tau + 2E}; exact FP32 re-rank -------------------------------------
     // Each selector thread buffers candidate indices in its slice of the scratch region and re-ranks them with exact
@@ -356,12 +366,17 @@ knn_wide_kernel(WideArgs a) {
             float dot[32];
             tmem_ld32(tmem_row + c0, dot);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                float v = fmaf(-2.f, dot[i], qn) + s_cn[c0 + i];
-                if (!a.normalize) v = fmaxf(v, 1e-12f);
-                if (v <= thr_b && m0 + c0 + i < a.M && valid) {
-                    s_coll[(half * cap2 + ncoll) * kWQ + ql] = m0 + c0 + i;
-                    if (++ncoll == cap2) { drain(); ++drains; }
+            for (int i4 = 0; i4 < 8; ++i4) {
+                const float4 cn4 = *reinterpret_cast<const float4*>(s_cn + c0 + 4 * i4);
+                const float cnv[4] = {cn4.x, cn4.y, cn4.z, cn4.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    float v = fmaf(-2.f, dot[4 * i4 + u], qn) + cnv[u];
+                    v = fmaxf(v, floor_d);
+                    if (v <= thr_b) {                                   // padding columns carry +inf, thr_b is finite
+                        s_coll[(half * cap2 + ncoll) * kWQ + ql] = m0 + c0 + 4 * i4 + u;
+                        if (++ncoll == cap2) { drain(); ++drains; }
+                    }
                 }
             }
         }
