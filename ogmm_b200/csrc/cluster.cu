@@ -35,7 +35,7 @@ extern "C" __attribute__((visibility("default"))) int ogmm_sinkhorn_cluster(cons
     OGMM_REQUIRE(B >= 0 && N >= 1 && J >= 1 && iters >= 1 && max_iter >= 1 && B < (1ll << 31), OGMM_EINVAL,
                  "ogmm_sinkhorn_cluster: bad sizes B=%lld N=%lld J=%lld iters=%lld max_iter=%lld", (long long)B,
                  (long long)N, (long long)J, (long long)iters, (long long)max_iter);
-    OGMM_REQUIRE(N <= kMaxPoints, OGMM_EUNSUPPORTED, "ogmm_sinkhorn_cluster: N=%lld > %lld", (long long)N, (long long)kMaxPoints);
+    OGMM_REQUIRE(N <= kMaxClusterPoints, OGMM_EUNSUPPORTED, "ogmm_sinkhorn_cluster: N=%lld > %lld", (long long)N, (long long)kMaxClusterPoints);
     OGMM_REQUIRE(J <= N && J <= 1024, OGMM_EUNSUPPORTED, "ogmm_sinkhorn_cluster: need J <= min(N, 1024), got J=%lld N=%lld",
                  (long long)J, (long long)N);
     OGMM_REQUIRE(iters <= 64 && max_iter <= 1024, OGMM_EUNSUPPORTED, "ogmm_sinkhorn_cluster: iters <= 64 and max_iter <= 1024");

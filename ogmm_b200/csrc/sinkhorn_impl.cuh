@@ -877,6 +877,10 @@ using namespace ogmm;
     } while (0)
 
 constexpr int64_t kMaxPoints = 8192;
+constexpr int64_t kMaxClusterPoints = 16384;      // clustering only: one extra (1024 threads x 16 points) variant
+
+// defined in cluster_big.cu (its own translation unit: the 16-points-per-thread body is slow to compile)
+int ogmm_launch_cluster_big(ogmm::SinkhornParams P, cudaStream_t s);
 
 template <int NT, int PPT, bool kCluster, bool kFast, bool kExactJ = false>
 static inline int launch_sinkhorn_variant(SinkhornParams P, cudaStream_t s) {
@@ -924,6 +928,7 @@ static inline int launch_sinkhorn(SinkhornParams P, void* workspace, int64_t wor
     int st = cuda_status(cudaMemsetAsync(ws, 0, 64, s), "cudaMemsetAsync(workspace header)");
     if (st != OGMM_OK) return st;
     if constexpr (kCluster) {
+        if (P.N > kMaxPoints) return ogmm_launch_cluster_big(P, s);
         if (P.J <= 16 && P.N <= 1024) {
             if (P.N <= 256) return launch_sinkhorn_variant<256, 1, true, true>(P, s);
             if (P.N <= 512) return launch_sinkhorn_variant<256, 2, true, true>(P, s);

@@ -270,7 +270,7 @@ def test_cluster_golden(og, golden):
         assert float((gam.cpu() - g["gamma"]).abs().max()) < 1e-3
 
 
-@pytest.mark.parametrize("n,j", [(1024, 16), (717, 16), (256, 8), (2048, 32), (1024, 128)])
+@pytest.mark.parametrize("n,j", [(1024, 16), (717, 16), (256, 8), (2048, 32), (1024, 128), (9000, 24)])
 def test_cluster_vs_oracle(og, orc, n, j):
     from ogmm_b200 import synth
     src, _, _, _ = synth.modelnet_batch(40, 3, n)
