@@ -206,6 +206,19 @@ def test_feature_moments_native_layout(og, orc, n, j, d):
     assert relerr(mu2, rmu) < 1e-5
 
 
+@pytest.mark.parametrize("n,d", [(1024, 512), (716, 256), (2048, 128)])
+def test_feature_moments_tensor_opt_in(og, orc, n, d, monkeypatch):
+    """OGMM_FEAT_TENSOR=1 routes J == 16 native-layout calls to the tcgen05 3xTF32 kernel: same FP32-level accuracy."""
+    g = torch.Generator().manual_seed(n + d)
+    gamma = torch.softmax(torch.randn(3, n, 16, generator=g) * 3, -1) * torch.rand(3, n, 1, generator=g)
+    feats = torch.relu(torch.randn(3, d, n, generator=g))
+    rpi, rmu = orc.gmm_moments(gamma.double(), feats.transpose(-1, -2).double())
+    monkeypatch.setenv("OGMM_FEAT_TENSOR", "1")
+    pi, mu = og.gmm_params(cu(gamma), cu(feats).transpose(-1, -2))
+    assert relerr(pi, rpi) < 1e-5
+    assert float(((mu.cpu().double() - rmu).abs() / rmu.abs().clamp(min=1e-3)).max()) < 1e-4
+
+
 def test_deepgmr_em_and_register(og, golden):
     g = golden("deepgmr")
     gam, pi, mu, sigma = og.deepgmr_em(cu(g["src_logits"]), cu(g["src"]))
