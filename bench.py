@@ -270,7 +270,7 @@ def run_ours(args):
     # "E/M-step % of HBM peak"); kNN and the Sinkhorn loop are instruction-issue bound
     # and are listed with the same arithmetic under "kernels"; "dominant_by_time" names the longest stage.
     hb = "feat_moments"
-    roofline = {"kernel": "gmm_moments_feat_kernel", "bound": "hbm", "achieved": kernels[hb]["achieved_gbs"], "peak": peak,
+    roofline = {"kernel": "gmm_moments_feat_tma_kernel", "bound": "hbm", "achieved": kernels[hb]["achieved_gbs"], "peak": peak,
                 "unit": "GB/s", "frac": kernels[hb]["frac_of_hbm_peak"], "traffic": traffic.get(hb), "peak_source": peak_src,
                 "launches_per_step": launches[hb], "ms_per_launch": stage_ms[hb] / launches[hb],
                 "dominant_by_time": max(stage_ms, key=stage_ms.get), "serial_ms_per_step": serial_ms,

@@ -17,7 +17,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libogmm_b200.so")
-SOURCES = ["capi.cu", "knn.cu", "knn_sweep.cu", "knn_wide.cu", "cluster.cu", "cluster_big.cu", "sinkhorn.cu", "moments.cu", "moments_tc.cu", "moments_mma.cu", "procrustes.cu"]
+SOURCES = ["capi.cu", "knn.cu", "knn_sweep.cu", "knn_wide.cu", "cluster.cu", "cluster_big.cu", "sinkhorn.cu", "moments.cu", "moments_tc.cu", "moments_tma.cu", "procrustes.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--extended-lambda", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",

@@ -436,7 +436,7 @@ softmax_moments_kernel(const float* __restrict__ logits, const float* __restrict
 
 using namespace ogmm;
 
-int ogmm_launch_moments_feat_mma(const float* gamma, int64_t g_sb, int64_t g_sn, int64_t g_sj,
+int ogmm_launch_moments_feat_tma(const float* gamma, int64_t g_sb, int64_t g_sn, int64_t g_sj,
                                  const float* feats, int64_t f_sb, int64_t f_sn, int64_t f_sd,
                                  int64_t B, int64_t N, int64_t J, int64_t D, float* pi_out, float* mu_out, cudaStream_t s);
 int ogmm_launch_moments_feat_tc(const float* gamma, int64_t g_sb, int64_t g_sn, int64_t g_sj,
@@ -454,15 +454,15 @@ extern "C" __attribute__((visibility("default"))) int ogmm_gmm_moments_feat(cons
     if (B == 0) return OGMM_OK;
     OGMM_REQUIRE(gamma && feats && mu_out, OGMM_EINVAL, "ogmm_gmm_moments_feat: null pointer");
     cudaStream_t s = as_stream(stream);
-    // J == 16, native (B,D,N) layout: features go HBM -> registers -> mma.sync 3xTF32 (moments_mma.cu); anything
-    // else, or OGMM_FEAT_NO_MMA=1, runs the FP32 FFMA2 kernel below.
+    // J == 16, native (B,D,N) layout: TMA -> shared -> mma.sync 3xTF32 pipeline (moments_tma.cu); OGMM_FEAT_NO_TMA=1
+    // drops to the FP32 FFMA2 kernel below, which also takes every other shape.
     // OGMM_FEAT_TENSOR=1 (checked first when set) opts into the tcgen05 3xTF32 kernel (moments_tc.cu; J == 16, native (B,D,N) layout).  It is
     // correct to FP32 accuracy but measured slower than the FP32 kernels on B200, so it is not
     // the default.
     {
-        const char* off = getenv("OGMM_FEAT_NO_MMA");
+        const char* off = getenv("OGMM_FEAT_NO_TMA");
         if (!(off && off[0] == '1')) {
-            const int st = ogmm_launch_moments_feat_mma(gamma, g_sb, g_sn, g_sj, feats, f_sb, f_sn, f_sd, B, N, J, D, pi_out,
+            const int st = ogmm_launch_moments_feat_tma(gamma, g_sb, g_sn, g_sj, feats, f_sb, f_sn, f_sd, B, N, J, D, pi_out,
                                                         mu_out, s);
             if (st != OGMM_EUNSUPPORTED) return st;
         }

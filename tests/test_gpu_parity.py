@@ -206,6 +206,25 @@ def test_feature_moments_native_layout(og, orc, n, j, d):
     assert relerr(mu2, rmu) < 1e-5
 
 
+@pytest.mark.parametrize("b,n,d", [(3, 1024, 512), (3, 1000, 96), (3, 36, 40), (2, 4096, 64), (3, 1024, 32), (3, 5000, 512),
+                                   (3, 2044, 288), (700, 128, 512), (301, 64, 224)])
+@pytest.mark.parametrize("path", ["tma", "ffma2"])
+def test_feature_moments_j16_kernels(og, orc, b, n, d, path, monkeypatch):
+    """The two J == 16 feature M-step kernels (TMA + mma.sync 3xTF32 pipeline, FP32 FFMA2) against the FP64 oracle, on
+    ragged point counts, row counts that do not fill a CTA tile, few and many items per CTA."""
+    g = torch.Generator().manual_seed(3 * n + d)
+    gamma = torch.softmax(torch.randn(b, n, 16, generator=g) * 3, -1) * torch.rand(b, n, 1, generator=g)
+    feats = torch.relu(torch.randn(b, d, n, generator=g)) + 0.01
+    rpi, rmu = orc.gmm_moments(gamma.double(), feats.transpose(-1, -2).double())
+    if path != "tma":
+        monkeypatch.setenv("OGMM_FEAT_NO_TMA", "1")
+    pi, mu = og.gmm_params(cu(gamma), cu(feats).transpose(-1, -2))
+    assert relerr(pi, rpi) < 1e-5
+    err = float(((mu.cpu().double() - rmu).abs() / rmu.abs().clamp(min=1e-3)).max())
+    print(f"\n  feature M-step {path} N={n} D={d}: max rel err {err:.2e}")
+    assert err < 2e-5
+
+
 @pytest.mark.parametrize("n,d", [(1024, 512), (716, 256), (2048, 128)])
 def test_feature_moments_tensor_opt_in(og, orc, n, d, monkeypatch):
     """OGMM_FEAT_TENSOR=1 routes J == 16 native-layout calls to the tcgen05 3xTF32 kernel: same FP32-level accuracy."""
