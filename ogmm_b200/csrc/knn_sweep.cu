@@ -36,10 +36,10 @@ struct TopK64 {
     int cnt;
     bool live;
     float* sd;
-    int* si;
+    unsigned short* si;                 // staged candidate indices: the sweep kernel takes M <= 4096
     int col;
 
-    __device__ __forceinline__ void init(float* stage_d, int* stage_i, int col_, bool live_) {
+    __device__ __forceinline__ void init(float* stage_d, unsigned short* stage_i, int col_, bool live_) {
 #pragma unroll
         for (int j = 0; j < K; ++j) key[j] = kEmptyKey;
         live = live_;
@@ -50,7 +50,7 @@ struct TopK64 {
     __device__ __forceinline__ void offer(float v, int idx) {
         if (v <= thr) {
             sd[cnt * kSwThreads + col] = v;
-            si[cnt * kSwThreads + col] = idx;
+            si[cnt * kSwThreads + col] = (unsigned short)idx;
             ++cnt;
         }
     }
@@ -85,9 +85,9 @@ struct TopK64 {
 // (key, index) bitonic sort, ascending, lexicographic; n is a power of two.
 __device__ __forceinline__ void bitonic_sort_pairs(float* key, int* val, int n) {
     for (int k = 2; k <= n; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int j = k >> 1, lj = 31 - __clz(k >> 1); j > 0; j >>= 1, --lj) {
             for (int t = threadIdx.x; t < (n >> 1); t += kSwThreads) {
-                const int i = ((t / j) * 2 * j) + (t % j);
+                const int i = ((t >> lj) << (lj + 1)) + (t & (j - 1));
                 const int l = i + j;
                 const bool up = ((i & k) == 0);
                 const float a = key[i], b = key[l];
@@ -110,7 +110,7 @@ struct SweepSmem {
 __host__ __device__ inline int pow2_ge(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 __host__ __device__ inline size_t sweep_smem_bytes(int N, int M, bool self) {
     const int Mp = pow2_ge(M), Np = self ? 0 : pow2_ge(N);
-    return (size_t)16 * M + (size_t)8 * Mp + (size_t)8 * Np + (size_t)8 * kSwStage * kSwThreads + 256;
+    return (size_t)16 * M + (size_t)8 * Mp + (size_t)8 * Np + (size_t)6 * kSwStage * kSwThreads + 256;
 }
 
 template <int K>
@@ -127,7 +127,7 @@ knn3_sweep_kernel(const float* __restrict__ src, int64_t s_sb, int64_t s_sn, int
     float* s_qkey = reinterpret_cast<float*>(s_cord + Mp);
     int* s_qord = reinterpret_cast<int*>(s_qkey + Np);
     float* s_stage_d = reinterpret_cast<float*>(s_qord + Np);
-    int* s_stage_i = reinterpret_cast<int*>(s_stage_d + kSwStage * kSwThreads);
+    unsigned short* s_stage_i = reinterpret_cast<unsigned short*>(s_stage_d + kSwStage * kSwThreads);
     float* s_red = reinterpret_cast<float*>(s_stage_i + kSwStage * kSwThreads);     // [64]
 
     const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -235,7 +235,7 @@ knn3_sweep_kernel(const float* __restrict__ src, int64_t s_sb, int64_t s_sn, int
                         v = fmaf(qy, c.y, v);
                         v = fmaf(qz, c.z, v);
                         v = fmaxf(__fadd_rn(__fadd_rn(v, qs), c.w), 1e-12f);
-                        if (v <= top.thr) { top.sd[top.cnt * kSwThreads + tid] = v; top.si[top.cnt * kSwThreads + tid] = s_cord[p]; ++top.cnt; }
+                        if (v <= top.thr) { top.sd[top.cnt * kSwThreads + tid] = v; top.si[top.cnt * kSwThreads + tid] = (unsigned short)s_cord[p]; ++top.cnt; }
                     }
                 }
                 L -= 4;
@@ -250,7 +250,7 @@ knn3_sweep_kernel(const float* __restrict__ src, int64_t s_sb, int64_t s_sn, int
                         v = fmaf(qy, c.y, v);
                         v = fmaf(qz, c.z, v);
                         v = fmaxf(__fadd_rn(__fadd_rn(v, qs), c.w), 1e-12f);
-                        if (v <= top.thr) { top.sd[top.cnt * kSwThreads + tid] = v; top.si[top.cnt * kSwThreads + tid] = s_cord[p]; ++top.cnt; }
+                        if (v <= top.thr) { top.sd[top.cnt * kSwThreads + tid] = v; top.si[top.cnt * kSwThreads + tid] = (unsigned short)s_cord[p]; ++top.cnt; }
                     }
                 }
                 R += 4;

@@ -24,6 +24,14 @@ def launches_per_step(iters=10):
 
 
 _side_streams = {}
+_copy_streams = {}
+
+
+def _copy_stream(device):
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    if key not in _copy_streams:
+        _copy_streams[key] = torch.cuda.Stream(device=key)
+    return _copy_streams[key]
 
 
 def _side_stream(device):
@@ -33,13 +41,19 @@ def _side_stream(device):
     return _side_streams[key]
 
 
-def _cloud_chain(x, feats, o, n_clusters, k, iters, timers, tag):
-    """kNN graph + edge features, clustering, feature M-step for one side (src or tgt) on the current stream."""
+def _cloud_chain(x, feats, o, n_clusters, k, iters, timers, tag, feats_ready=None):
+    """kNN graph + edge features, clustering, feature M-step for one side (src or tgt) on the current stream.
+
+    ``feats_ready``: optional CUDA event after which ``feats`` may be read (its host-to-device copy); only the
+    feature M-step waits on it, the kNN graph and the clustering need xyz and the overlap scores alone.
+    """
     pts = x.transpose(-1, -2)
     with _Stage(timers, "knn_edge"):
         edge = ops.knn_graph(pts, pts, k, want_edge=True)[2].permute(0, 3, 1, 2)
     with _Stage(timers, "cluster"):
         gam, pi, mu, _ = ops.sinkhorn_cluster(pts, o, n_clusters, iters=iters)
+    if feats_ready is not None:
+        torch.cuda.current_stream(x.device).wait_event(feats_ready)
     with _Stage(timers, "feat_moments"):
         nf = ops.gmm_moments(gam, feats.transpose(-1, -2))[1]
     return edge, gam, pi, mu, nf
@@ -47,7 +61,7 @@ def _cloud_chain(x, feats, o, n_clusters, k, iters, timers, tag):
 
 @torch.no_grad()
 def register_hot_path(src, tgt, src_feats, tgt_feats, src_o, tgt_o, n_clusters=16, k=20, iters=10, timers=None,
-                      overlap=True):
+                      overlap=True, feats_ready=(None, None)):
     """src, tgt (B,3,N|M); *_feats (B,D,N|M); *_o (B,N|M)  ->  dict with rot (B,3,3), trans (B,3),
     edge_src/edge_tgt (B,6,N,k) views, and the GMM parameters of both clouds.
 
@@ -55,20 +69,26 @@ def register_hot_path(src, tgt, src_feats, tgt_feats, src_o, tgt_o, n_clusters=1
     chain runs on a side stream next to the source chain (their kernels share the SMs; neither fills the
     GPU alone at moderate batch sizes).  ``timers``: optional dict stage -> list of (start, end) CUDA events
     recorded on the stream each stage runs on; pass ``overlap=False`` to time the kernels in isolation.
+    ``feats_ready``: optional (src, tgt) CUDA events gating the first read of ``src_feats`` / ``tgt_feats``
+    (``register_from_host`` copies them while the kNN graph and the clustering already run).
     """
     cur = torch.cuda.current_stream(src.device)
     if overlap:
         side = _side_stream(src.device)
         side.wait_stream(cur)
         with torch.cuda.stream(side):
-            edge_t, gam_t, pi_t, mu_t, nf_t = _cloud_chain(tgt, tgt_feats, tgt_o, n_clusters, k, iters, timers, "tgt")
-        edge_s, gam_s, pi_s, mu_s, nf_s = _cloud_chain(src, src_feats, src_o, n_clusters, k, iters, timers, "src")
+            edge_t, gam_t, pi_t, mu_t, nf_t = _cloud_chain(tgt, tgt_feats, tgt_o, n_clusters, k, iters, timers, "tgt",
+                                                           feats_ready[1])
+        edge_s, gam_s, pi_s, mu_s, nf_s = _cloud_chain(src, src_feats, src_o, n_clusters, k, iters, timers, "src",
+                                                       feats_ready[0])
         cur.wait_stream(side)
         for t in (edge_t, gam_t, pi_t, mu_t, nf_t):
             t.record_stream(cur)
     else:
-        edge_s, gam_s, pi_s, mu_s, nf_s = _cloud_chain(src, src_feats, src_o, n_clusters, k, iters, timers, "src")
-        edge_t, gam_t, pi_t, mu_t, nf_t = _cloud_chain(tgt, tgt_feats, tgt_o, n_clusters, k, iters, timers, "tgt")
+        edge_s, gam_s, pi_s, mu_s, nf_s = _cloud_chain(src, src_feats, src_o, n_clusters, k, iters, timers, "src",
+                                                       feats_ready[0])
+        edge_t, gam_t, pi_t, mu_t, nf_t = _cloud_chain(tgt, tgt_feats, tgt_o, n_clusters, k, iters, timers, "tgt",
+                                                       feats_ready[1])
     with _Stage(timers, "procrustes"):
         rot, trans, corr, _ = ops.soft_procrustes(mu_s, mu_t, nf_s, nf_t, 0.05)
     return {"rot": rot, "trans": trans, "edge_src": edge_s, "edge_tgt": edge_t, "src_gamma": gam_s, "tgt_gamma": gam_t,
@@ -99,12 +119,30 @@ def register_from_host(host, device, n_clusters=16, k=20, iters=10):
 
     ``host`` maps src, tgt, src_feats, tgt_feats, src_o, tgt_o to pinned CPU tensors.  Returns
     (rot, trans) as CPU tensors plus the bytes moved in each direction.
+
+    The small inputs (xyz, overlap scores: 8 MB at B=256) go first on the caller's stream; the two feature tensors
+    (2 x 537 MB) follow on a copy stream, and only the feature M-step of each side waits for its tensor, so the kNN
+    graph and the clustering of the WHOLE batch run under the copies.  The batch is not chunked: the Sinkhorn early
+    exit is a mean over the batch (lib/utils.py:99-102) and chunking would change the iteration schedule.
     """
-    dev = {n: host[n].to(device, non_blocking=True) for n in ("src", "tgt", "src_feats", "tgt_feats", "src_o", "tgt_o")}
+    names = ("src", "tgt", "src_feats", "tgt_feats", "src_o", "tgt_o")
+    cur = torch.cuda.current_stream(device)
+    copy = _copy_stream(device)
+    dev = {n: host[n].to(device, non_blocking=True) for n in ("src", "tgt", "src_o", "tgt_o")}
+    ready = []
+    copy.wait_stream(cur)
+    with torch.cuda.stream(copy):
+        for n in ("src_feats", "tgt_feats"):
+            dev[n] = host[n].to(device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy)
+            ready.append(ev)
+    dev["src_feats"].record_stream(cur)
+    dev["tgt_feats"].record_stream(_side_stream(device))
     out = register_hot_path(dev["src"], dev["tgt"], dev["src_feats"], dev["tgt_feats"], dev["src_o"], dev["tgt_o"],
-                            n_clusters, k, iters)
+                            n_clusters, k, iters, feats_ready=tuple(ready))
     rot, trans = out["rot"].cpu(), out["trans"].cpu()
-    h2d = sum(host[n].numel() * host[n].element_size() for n in dev)
+    h2d = sum(host[n].numel() * host[n].element_size() for n in names)
     d2h = rot.numel() * 4 + trans.numel() * 4
     return rot, trans, h2d, d2h
 

@@ -408,3 +408,19 @@ def test_full_size_properties(og):
     assert torch.allclose(torch.det(rot), torch.ones(256, device=DEV), atol=1e-5)
     eye = torch.eye(3, device=DEV).expand(256, 3, 3)
     assert float((rot @ rot.transpose(1, 2) - eye).abs().max()) < 1e-5
+
+
+def test_register_from_host_matches_device_path(og):
+    """The host-buffer entry point (feature copies overlapped with kNN + clustering) returns exactly what the
+    device-resident call returns, repeatedly (stream / allocator reuse across calls)."""
+    from ogmm_b200 import pipeline, synth
+    host = synth.hot_path_inputs(0, 24, 1024, 256)
+    pinned = {k: torch.from_numpy(np.ascontiguousarray(host[k])).float().pin_memory()
+              for k in ("src", "tgt", "src_feats", "tgt_feats", "src_o", "tgt_o")}
+    d = {k: v.cuda() for k, v in pinned.items()}
+    ref = pipeline.register_hot_path(d["src"], d["tgt"], d["src_feats"], d["tgt_feats"], d["src_o"], d["tgt_o"], 16, 20)
+    torch.cuda.synchronize()
+    for _ in range(3):
+        rot, trans, h2d, d2h = pipeline.register_from_host(pinned, torch.device("cuda:0"), 16, 20)
+        assert torch.equal(rot, ref["rot"].cpu()) and torch.equal(trans, ref["trans"].cpu())
+    assert h2d == sum(v.numel() * 4 for v in pinned.values()) and d2h == 24 * 12 * 4
