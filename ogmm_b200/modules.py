@@ -12,6 +12,7 @@ import torch
 from torch import nn
 
 from . import ops
+from ._guard import forward_only
 from .se3 import compute_rigid_transformation
 from .utils import wkeans_plus
 
@@ -38,7 +39,7 @@ class GMMSVD(nn.Module):
         self.is_sk = is_sk
         self.epsilon = epsilon
 
-    @torch.no_grad()
+    @forward_only
     def forward(self, src, tgt, src_desc, tgt_desc, src_pi, tgt_pi):
         batch_size = src.size(0)
         if not self.is_sk:
@@ -54,20 +55,20 @@ class GMMSVD(nn.Module):
         return R, t.view(batch_size, 3), src_corr, tgt.transpose(-1, -2)
 
 
-@torch.no_grad()
+@forward_only
 def graph_features(x, k=20):
     """models/dgcnn.py:135-137 in one launch: x (B,3,N) -> (B,6,N,k) edge tensor fed to conv1."""
     pts = x.transpose(-1, -2)
     return ops.knn_graph(pts, pts, k, want_edge=True)[2].permute(0, 3, 1, 2)
 
 
-@torch.no_grad()
+@forward_only
 def gmm_register(pi_s, mu_s, mu_t, sigma_t):
     """baseline/deepgmr.py:17-38 -> (B,4,4); no host SVD and no hard-coded ``.cuda()``."""
     return ops.gmm_register(pi_s, mu_s, mu_t, sigma_t)
 
 
-@torch.no_grad()
+@forward_only
 def deepgmr_em(logits, pts):
     """baseline/deepgmr.py:71-74 fused: logits (B,J,N), pts (B,3,N) -> gamma (B,J,N), pi, mu, sigma."""
     return ops.softmax_moments(logits, pts)

@@ -8,6 +8,7 @@ from __future__ import annotations
 import torch
 
 from . import ops
+from ._guard import forward_only
 
 __all__ = ["decompose_trans", "integrate_trans", "torch_identity", "torch_inverse", "torch_concatenate",
            "torch_transform", "compute_rigid_transformation"]
@@ -64,7 +65,7 @@ def torch_transform(g, a, normals=None):
     return b
 
 
-@torch.no_grad()
+@forward_only
 def compute_rigid_transformation(src, src_corr, weight):
     """lib/se3.py:256-289.  src, src_corr (B,3,n), weight (B,1,n) -> R (B,3,3), t (B,3,1)."""
     rot, t = ops.rigid_transform(src, src_corr, weight)

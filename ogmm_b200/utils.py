@@ -3,13 +3,16 @@ argument meaning, return shapes and dtypes), computed by the sm_100a kernels.
 
 Each function cites the reference lines it replaces.  Inputs must be CUDA float32 tensors (views
 are fine); results come back on the same device and stream.  Forward / inference only: outputs do
-not carry autograd history ("Autograd").
+not carry autograd history ("Autograd"), and a call that autograd would have
+to record (grad mode on, an input requiring grad) raises instead of returning gradient-less tensors
+(``_guard.forward_only``; ``knn`` and ``farthest_point_sample`` return indices and are exempt).
 """
 from __future__ import annotations
 
 import torch
 
 from . import ops
+from ._guard import forward_only
 
 __all__ = ["square_distance", "knn", "get_graph_feature", "sinkhorn", "index_points", "gmm_params",
            "og_params", "farthest_point_sample", "cos_similarity", "get_local_corrs", "get_anchor_corrs",
@@ -40,7 +43,7 @@ def knn(src, tgt, k, normalize=False):
     return ops.knn_graph(src, tgt, k, normalize)[0]
 
 
-@torch.no_grad()
+@forward_only
 def get_graph_feature(x, k=20, idx=None, extra_dim=False):
     """lib/utils.py:47-66.  x (B,C,N) -> (B,2C,N,k) view over (B,N,k,2C) memory, [x_j - x_i ; x_i].
 
@@ -59,7 +62,7 @@ def get_graph_feature(x, k=20, idx=None, extra_dim=False):
     return edge.permute(0, 3, 1, 2)
 
 
-@torch.no_grad()
+@forward_only
 def sinkhorn(cost, p=None, q=None, epsilon=1e-2, thresh=1e-2, max_iter=100):
     """lib/utils.py:74-108.  Log-domain Sinkhorn -> (gamma (B,N,M), mean_b sum gamma*cost)."""
     gamma, loss, _ = ops.sinkhorn(cost, p, q, epsilon, thresh, max_iter)
@@ -75,13 +78,13 @@ def index_points(points, idx):
     return points[bidx, idx, :]
 
 
-@torch.no_grad()
+@forward_only
 def gmm_params(gamma, pts, return_sigma=False):
     """lib/utils.py:130-149.  gamma (B,N,J), pts (B,N,D) -> pi (B,J), mu (B,J,D) [, sigma (B,J,D,D)]."""
     return ops.gmm_moments(gamma, pts, return_sigma)
 
 
-@torch.no_grad()
+@forward_only
 def og_params(pts, gamma, o_score=None, feature=None):
     """lib/utils.py:152-167.  Overlap-guided moments with the extra (J+1)-th non-overlap component."""
     if o_score is not None:
@@ -104,20 +107,20 @@ def farthest_point_sample(xyz, npoint, is_center=False):
     return ops.fps(xyz, npoint, start)[0]
 
 
-@torch.no_grad()
+@forward_only
 def cos_similarity(x, y):
     """lib/utils.py:222-226.  (B,N,D), (B,M,D) -> (B,N,M)."""
     return ops.cos_similarity(x, y)
 
 
-@torch.no_grad()
+@forward_only
 def get_local_corrs(xyz, xyz_mu, feats):
     """lib/utils.py:244-254.  Feature of the point nearest to each anchor: 1-NN through the kNN kernel."""
     idx = ops.knn_graph(xyz_mu, xyz, 1)[0]                       # (B,S,1)
     return torch.gather(feats, dim=1, index=idx.repeat(1, 1, feats.size(-1)))
 
 
-@torch.no_grad()
+@forward_only
 def get_anchor_corrs(xyz, feats, num_clusters, dst='eu', iters=10, is_fast=True):
     """lib/utils.py:257-266, ``is_fast=True`` branch (the only one the model takes).  xyz (B,3,N), feats (B,D,N)."""
     if not is_fast:
@@ -130,7 +133,7 @@ def get_anchor_corrs(xyz, feats, num_clusters, dst='eu', iters=10, is_fast=True)
     return feats_anchor, feats_pos, xyz_mu.transpose(-1, -2)
 
 
-@torch.no_grad()
+@forward_only
 def wkeans_plus(xyz, feats, o_scores, n_clusters, iters=10, tau=1.0):
     """lib/utils.py:269-291.  xyz (B,N,3), feats (B,N,D) (a view of (B,D,N) is read in place), o (B,N)
     -> gamma (B,N,J), pi (B,J), node_xyz (B,J,3), node_feats (B,J,D)."""

@@ -38,3 +38,26 @@ def test_install_rebinds_every_import_site_and_uninstall_restores():
         assert models.dgcnn.knn is orig_knn and models.gmmreg.wkeans_plus is orig_wk
     finally:
         sys.path.remove(REF)
+
+
+def test_forward_only_guard_is_loud():
+    """Differentiable reference functions refuse inputs that need a backward pass instead of dropping the graph;
+    the check runs before anything touches CUDA, so it is testable here."""
+    import pytest
+    import torch
+    from ogmm_b200 import utils, modules, se3
+    g = torch.rand(2, 32, 4, requires_grad=True)
+    x = torch.rand(2, 32, 8)
+    with pytest.raises(RuntimeError, match="forward-only"):
+        utils.gmm_params(g, x)
+    with pytest.raises(RuntimeError, match="forward-only"):
+        utils.gmm_params(g.detach(), x.requires_grad_())
+    with pytest.raises(RuntimeError, match="forward-only"):
+        se3.compute_rigid_transformation(torch.rand(2, 3, 8, requires_grad=True), torch.rand(2, 3, 8), torch.rand(2, 1, 8))
+    with pytest.raises(RuntimeError, match="forward-only"):
+        modules.GMMSVD(is_sk=False)(torch.rand(2, 4, 3), torch.rand(2, 4, 3), torch.rand(2, 4, 8, requires_grad=True),
+                                    torch.rand(2, 4, 8), torch.rand(2, 4), torch.rand(2, 4))
+    # without a graph to record, the same call goes on to the kernels (and, on this CPU box, to the CUDA-only check)
+    with torch.no_grad():
+        with pytest.raises(TypeError, match="CUDA"):
+            utils.gmm_params(g, x)
