@@ -94,9 +94,13 @@ int ogmm_fps(const float* xyz, int64_t sb, int64_t sn, int64_t sc, int64_t B, in
  *   xyz (B,N,3) strided view; o_scores (B,N) contiguous.
  *   gamma_out (B,N,J), pi_out (B,J), mu_out (B,J,3) contiguous.
  *   The batch-coupled early exit (:99-102) is reproduced exactly: each launch records every
- *   cloud's per-iteration change, the last CTA to finish evaluates the batch means, and up to
- *   `iters` follow-up launches (queued on the same stream, immediate exit when not needed) re-run
- *   from the first outer iteration whose inner count changed.  No host synchronisation.
+ *   cloud's per-iteration change, the last CTA to finish evaluates the batch means, and one
+ *   persistent follow-up launch (queued on the same stream, immediate exit when not needed) re-runs
+ *   from the first outer iteration whose inner count changed until the schedule stands.  No host
+ *   synchronisation, no cooperative launch.  The follow-up synchronises its blocks through a
+ *   barrier in the workspace and is sized so that two of them (the source and the target call of a
+ *   pair, on two streams) can always be resident together; do not keep more than two clustering
+ *   calls in flight on one device at the same time.
  *   workspace: device scratch of at least ogmm_sinkhorn_cluster_workspace(...) bytes; contents
  *   need not be initialised.  iters_run_out (optional) (iters) int32: inner iterations per outer. */
 int64_t ogmm_sinkhorn_cluster_workspace(int64_t B, int64_t N, int64_t J, int64_t iters, int64_t max_iter);

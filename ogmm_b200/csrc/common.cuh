@@ -64,6 +64,13 @@ __device__ __forceinline__ float block_sum(float v, float* scratch) {
     return warp_sum(r);
 }
 
+// Packed FP32 FMA (sm_100 FFMA2): d.x += a.x * b.x, d.y += a.y * b.y in one issue slot.
+__device__ __forceinline__ void ffma2_pair(float2& d, const float2 a, const float2 b) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;"
+        : "+l"(*reinterpret_cast<unsigned long long*>(&d))
+        : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)));
+}
+
 constexpr int kJC = 16;                 // column chunk held in registers
 
 // ---- 16-column butterfly: every lane enters with 16 partial sums, lane l leaves with the warp

@@ -31,13 +31,12 @@
 // through the exit test.  The main launch runs every Sinkhorn call for max_iter iterations and records
 // each cloud's change per (outer, inner) iteration; the last CTA to finish evaluates the batch means in
 // order and, at the first (outer o, inner i) with mean < thresh and i+1 below the count that was run,
-// stores n_inner[o] = i+1 and resume = o.  ONE follow-up launch is always queued: a persistent
-// cooperative kernel that returns at once when nothing has to change (the common case) and otherwise
-// re-runs from the centroids saved at the start of outer iteration `resume`, re-evaluates, and repeats
-// behind a grid barrier until the schedule is certified.  The result is bit-identical to running the
+// stores n_inner[o] = i+1 and resume = o.  ONE follow-up launch is always queued: a persistent kernel
+// (ordinary launch, grid <= co-resident capacity) that returns at once when nothing has to change (the
+// common case) and otherwise re-runs from the centroids saved at the start of outer iteration `resume`,
+// re-evaluates, and repeats behind a software grid barrier until the schedule is certified.  The result is bit-identical to running the
 // exit test inline, and deterministic (fixed-order reductions, no float atomics).
 #pragma once
-#include <cooperative_groups.h>
 
 #include "common.cuh"
 
@@ -52,7 +51,7 @@ struct ClusterWsLayout {
 __host__ __device__ inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 __host__ __device__ inline ClusterWsLayout cluster_ws_layout(int64_t B, int64_t J, int64_t iters, int64_t max_iter) {
     ClusterWsLayout l;
-    l.state_off = 0;                                         // int32[16]: [0]=resume [1]=done counter [2]=rescues
+    l.state_off = 0;                                         // int32[16]: [0]=resume [1]=done counter [2]=rescues [3],[4]=grid barrier
     l.ninner_off = 64;                                       // int32[iters]
     l.means_off = align_up(l.ninner_off + 4 * iters, 256);   // float[iters][max_iter] batch means
     l.diffs_off = align_up(l.means_off + 4 * iters * max_iter, 256);   // float[iters][max_iter][B]
@@ -495,19 +494,23 @@ __device__ __forceinline__ void process_cloud(const SinkhornParams& P, const Sme
             __syncthreads();
             bool tripped = false;
             for (int it = 0; it < n_it; ++it) {
+                // row sums r_i = sum_j G_ij b_j and, below, column sums sum_i G_ij a_i as packed FFMA2 on column pairs
                 float r[PPT];
+                {
+                    float2 r2[PPT];
 #pragma unroll
-                for (int p = 0; p < PPT; ++p) r[p] = 0.f;
+                    for (int p = 0; p < PPT; ++p) r2[p] = make_float2(0.f, 0.f);
 #pragma unroll
-                for (int j4 = 0; j4 < JF / 4; ++j4) {
-                    const float4 bq = *reinterpret_cast<const float4*>(S.bq + 4 * j4);
+                    for (int j4 = 0; j4 < JF / 4; ++j4) {
+                        const float4 bq = *reinterpret_cast<const float4*>(S.bq + 4 * j4);
 #pragma unroll
-                    for (int p = 0; p < PPT; ++p) {
-                        r[p] = fmaf(G[p][4 * j4 + 0], bq.x, r[p]);
-                        r[p] = fmaf(G[p][4 * j4 + 1], bq.y, r[p]);
-                        r[p] = fmaf(G[p][4 * j4 + 2], bq.z, r[p]);
-                        r[p] = fmaf(G[p][4 * j4 + 3], bq.w, r[p]);
+                        for (int p = 0; p < PPT; ++p) {
+                            ffma2_pair(r2[p], make_float2(G[p][4 * j4 + 0], G[p][4 * j4 + 1]), make_float2(bq.x, bq.y));
+                            ffma2_pair(r2[p], make_float2(G[p][4 * j4 + 2], G[p][4 * j4 + 3]), make_float2(bq.z, bq.w));
+                        }
                     }
+#pragma unroll
+                    for (int p = 0; p < PPT; ++p) r[p] = r2[p].x + r2[p].y;
                 }
                 float du_abs = 0.f;
 #pragma unroll
@@ -521,11 +524,11 @@ __device__ __forceinline__ void process_cloud(const SinkhornParams& P, const Sme
                 }
                 float part[JF];
 #pragma unroll
-                for (int j = 0; j < JF; ++j) {
-                    float acc = 0.f;
+                for (int j2 = 0; j2 < JF / 2; ++j2) {
+                    float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
-                    for (int p = 0; p < PPT; ++p) acc = fmaf(G[p][j], a[p], acc);
-                    part[j] = acc;
+                    for (int p = 0; p < PPT; ++p) ffma2_pair(acc, make_float2(G[p][2 * j2], G[p][2 * j2 + 1]), make_float2(a[p], a[p]));
+                    part[2 * j2] = acc.x; part[2 * j2 + 1] = acc.y;
                 }
                 const float tot = butterfly16(part, lane);
                 if ((lane & 1) == 0) S.wtot[warp * JF + ((lane >> 1) & 15)] = tot;
@@ -820,9 +823,32 @@ __device__ __forceinline__ void verify_schedule(const SinkhornParams& P, int res
     __syncthreads();
 }
 
+// Grid-wide barrier of the follow-up launch: arrive counter + generation in the workspace header.  The launch is an
+// ordinary one with grid <= the kernel's co-resident capacity, NOT a cooperative launch: a cooperative launch has to
+// wait until the whole grid fits at once, which stalls it behind whatever the other stream of a pair is running
+// (measured: step time bimodal 1.47 / 1.86 ms with it, 1.44 ms without).  Blocks that find nothing to redo return
+// before touching the barrier -- the common case -- and those that do spin are all scheduled eventually, because the
+// kernels they share the GPU with never wait on this stream.
+__device__ __forceinline__ void grid_barrier(int32_t* count, int32_t* gen, int nblocks) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const int g = *reinterpret_cast<volatile int32_t*>(gen);
+        if (atomicAdd(count, 1) == nblocks - 1) {
+            atomicExch(count, 0);
+            __threadfence();
+            atomicAdd(gen, 1);
+        } else {
+            while (*reinterpret_cast<volatile int32_t*>(gen) == g) __nanosleep(100);
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
 // mode 0: main launch, one CTA per cloud, last CTA to finish evaluates the exit test.
-// mode 1: persistent cooperative follow-up; returns at once when the schedule of the main launch stands.
-// (One kernel for both so the cloud body is instantiated once.)
+// mode 1: persistent follow-up (grid <= co-resident capacity); returns at once when the schedule of the main launch
+// stands.  (One kernel for both so the cloud body is instantiated once.)
 template <int NT, int PPT, bool kCluster, bool kFast, bool kExactJ>
 __global__ void __launch_bounds__(NT, (kFast && NT == 256) ? 2 : 1)
 sinkhorn_kernel(SinkhornParams P, int mode) {
@@ -832,7 +858,6 @@ sinkhorn_kernel(SinkhornParams P, int mode) {
         resume = __ldcg(P.state);
         if (resume >= P.iters) return;
     }
-    namespace cg = cooperative_groups;
     const int Jp = kFast ? 16 : (P.J + kJC - 1) / kJC * kJC;
     const Smem S = carve_smem<NT>(smem_raw, Jp);
     while (resume < P.iters) {
@@ -851,11 +876,10 @@ sinkhorn_kernel(SinkhornParams P, int mode) {
             }
             return;
         }
-        cg::grid_group grid = cg::this_grid();
-        grid.sync();
+        grid_barrier(P.state + 3, P.state + 4, (int)gridDim.x);
         if (blockIdx.x == 0) verify_schedule<NT>(P, resume, false);
         __threadfence();
-        grid.sync();
+        grid_barrier(P.state + 3, P.state + 4, (int)gridDim.x);
         resume = __ldcg(P.state);
     }
 }
@@ -895,7 +919,10 @@ static inline int launch_sinkhorn_variant(SinkhornParams P, cudaStream_t s) {
     kern<<<(unsigned)P.B, NT, smem, s>>>(P, 0);
     st = cuda_status(cudaGetLastError(), "sinkhorn_kernel (main launch)");
     if (st != OGMM_OK) return st;
-    // co-resident grid for the cooperative follow-up
+    // Follow-up grid: one CTA per SM.  The kernel fits at least one CTA per SM, so TWO such grids are always
+    // co-resident together -- the source and target calls of a pair may both sit in their barrier at once without
+    // starving each other (a spinning block keeps its SM slot).  More than two clustering calls of one device in
+    // flight at the same time, all of them hitting the early exit, is outside this guarantee (include/ogmm_b200.h).
     int dev = 0, sms = 0, per_sm = 0;
     st = cuda_status(cudaGetDevice(&dev), "cudaGetDevice");
     if (st != OGMM_OK) return st;
@@ -904,12 +931,11 @@ static inline int launch_sinkhorn_variant(SinkhornParams P, cudaStream_t s) {
     st = cuda_status(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem), "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
     if (st != OGMM_OK) return st;
     OGMM_REQUIRE(per_sm >= 1, OGMM_ECUDA, "sinkhorn fix-up kernel does not fit on an SM");
-    int grid = sms * per_sm;
+    int grid = per_sm >= 2 ? sms : sms / 2;
     if (grid > P.B) grid = P.B;
-    int mode = 1;
-    void* args[] = {&P, &mode};
-    st = cuda_status(cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)grid), dim3(NT), args, smem, s), "sinkhorn_kernel (follow-up launch)");
-    return st;
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, NT, smem, s>>>(P, 1);
+    return cuda_status(cudaGetLastError(), "sinkhorn_kernel (follow-up launch)");
 }
 
 template <bool kCluster>

@@ -313,6 +313,54 @@ def test_cluster_vs_oracle(og, orc, n, j):
     check_cluster(og, orc, xyz, feats, o, j)
 
 
+@pytest.mark.parametrize("n,j,scale,tau", [(1024, 16, 0.03, 1.0), (717, 16, 0.01, 1.0), (1024, 16, 1.0, 30.0), (2048, 32, 0.03, 1.0)])
+def test_cluster_early_exit_every_outer_iteration(og, orc, n, j, scale, tau):
+    """Flat costs (tiny clouds or a large tau) make the batch-mean exit test fire in every outer iteration, so the
+    follow-up launch has to re-run from the saved centroids several times; the inner-iteration counts and the
+    results must still be the reference's."""
+    from ogmm_b200 import synth
+    src, _, _, _ = synth.modelnet_batch(11, 5, n)
+    xyz = torch.from_numpy(src).transpose(1, 2).contiguous() * scale
+    g = torch.Generator().manual_seed(n + j)
+    feats = torch.relu(torch.randn(5, 32, n, generator=g))
+    o = torch.sigmoid(torch.randn(5, n, generator=g))
+    tr = []
+    rg, rpi, rmu, rnf = orc.sinkhorn_kmeans(xyz, feats.transpose(-1, -2), o, j, tau=tau, trace=tr)
+    assert min(tr) < 10, "inputs no longer trigger the early exit"
+    gam, pi, mu, nf = og.wkeans_plus(cu(xyz), cu(feats).transpose(-1, -2), cu(o), j, iters=10, tau=tau)
+    run = og.ops.sinkhorn_cluster(cu(xyz), cu(o), j, tau=tau, want_iters=True)[3]
+    assert run.cpu().tolist() == tr
+    sc = float(rmu.abs().max())
+    assert float((mu.cpu() - rmu).abs().max()) / sc < 1e-4 and relerr(pi, rpi) < 1e-4
+    assert float((nf.cpu() - rnf).abs().max() / rnf.abs().max()) < 1e-4 and float((gam.cpu() - rg).abs().max()) < 1e-3
+
+
+@pytest.mark.timeout(120, method="thread")
+def test_cluster_follow_ups_of_two_streams_do_not_starve_each_other(og):
+    """Source and target clustering run on two streams; when both hit the early exit their follow-up kernels sit
+    in grid barriers at the same time.  Results must equal the one-stream results (and the test must finish)."""
+    from ogmm_b200 import synth
+    src, tgt, _, _ = synth.modelnet_batch(21, 64, 1024)
+    xs = cu(torch.from_numpy(src).transpose(1, 2).contiguous() * 0.03)
+    xt = cu(torch.from_numpy(tgt).transpose(1, 2).contiguous() * 0.03)
+    g = torch.Generator().manual_seed(5)
+    os_, ot = cu(torch.sigmoid(torch.randn(64, 1024, generator=g))), cu(torch.sigmoid(torch.randn(64, 1024, generator=g)))
+    ref_s = og.ops.sinkhorn_cluster(xs, os_, 16, want_iters=True)
+    ref_t = og.ops.sinkhorn_cluster(xt, ot, 16, want_iters=True)
+    assert min(ref_s[3].tolist()) < 10 and min(ref_t[3].tolist()) < 10
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    for _ in range(5):
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            out_t = og.ops.sinkhorn_cluster(xt, ot, 16, want_iters=True)
+        out_s = og.ops.sinkhorn_cluster(xs, os_, 16, want_iters=True)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        for a, b in zip(out_s + out_t, ref_s + ref_t):
+            assert torch.equal(a, b)
+
+
 def test_cluster_metre_scale_and_strided_xyz(og, orc):
     from ogmm_b200 import synth
     src, _, _, _ = synth.icl_nuim_batch(3, 2, 1024)
