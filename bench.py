@@ -52,13 +52,31 @@ class ClockSampler:
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
+    """One ``nvidia-smi -lms`` child for the whole run.  It is started BEFORE the warm-up and the timed region only
+    begins once it has delivered a sample: nvidia-smi's own start-up (NVML attach, a cold binary on a fresh box)
+    holds driver locks for up to a few hundred ms and stalls kernel launches -- started right at the timed region it
+    made the measured step time swing between 1.4 and 6.3 ms.  Only samples taken inside the timed region are kept.
+    """
+
     def __init__(self, gpu_index):
         self.gpu_index, self.rows, self.proc = gpu_index, [], None
+        self.lo, self.hi = 0, None
+
+    def wait_ready(self, timeout=10.0):
+        t0 = time.time()
+        while self.proc is not None and not self.rows and time.time() - t0 < timeout:
+            time.sleep(0.02)
+
+    def begin(self):
+        self.lo = len(self.rows)
+
+    def end(self):
+        self.hi = len(self.rows)
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.gpu_index), "-lms", "50"], stdout=subprocess.PIPE,
+                                          "-i", str(self.gpu_index), "-lms", "100"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -79,7 +97,8 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, reasons, power = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = self.rows[self.lo:self.hi] or self.rows[-3:]     # a region shorter than the period: the closest samples
+        for r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 9:
                 continue
@@ -204,30 +223,47 @@ def run_ours(args):
     host = {k: torch.from_numpy(v) for k, v in h.items()}
     d = {k: v.to(dev) for k, v in host.items()}
 
-    def step(timers=None, overlap=not args.no_overlap):
+    def eager_step(timers=None, overlap=not args.no_overlap):
         return pipeline.register_hot_path(d["src"], d["tgt"], d["src_feats"], d["tgt_feats"], d["src_o"], d["tgt_o"],
                                           N_CLUSTERS, KNN, ITERS, timers, overlap)
+
+    # The timed step replays the two-stream step captured into a CUDA graph over the resident inputs (one launch per
+    # step, immune to host jitter); --no-graph / --no-overlap time the eager call instead.
+    graphed = None
+    if not (args.no_graph or args.no_overlap):
+        graphed = pipeline.GraphedHotPath(d["src"], d["tgt"], d["src_feats"], d["tgt_feats"], d["src_o"], d["tgt_o"],
+                                          N_CLUSTERS, KNN, ITERS)
+
+    def step(timers=None, overlap=not args.no_overlap):
+        if graphed is not None and timers is None and overlap:
+            return graphed.replay()
+        return eager_step(timers, overlap)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        out = step()
-    barrier()
-
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        out = step()
+    barrier()
+    if rank == 0:
+        sampler.wait_ready()
+
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.begin()
     e0.record()
     for _ in range(args.steps):
         out = step()
     e1.record()
     barrier()
-    elapsed_ms = e0.elapsed_time(e1)
+    sampler.end()
+    clocks = sampler.stop() if rank == 0 else None          # samples taken inside the timed region; the poller is gone
+    elapsed_ms = e0.elapsed_time(e1)                        # before the per-stage pass below
 
     t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
     if world > 1:
@@ -248,7 +284,6 @@ def run_ours(args):
     s1.record()
     barrier()
     serial_ms = s0.elapsed_time(s1) / args.steps
-    clocks = sampler.stop() if rank == 0 else None          # sampled across both passes (GPU busy throughout)
     stage_ms = {s: sum(a.elapsed_time(b) for a, b in ev) / args.steps for s, ev in timers.items()}
     ab = algorithmic_bytes()
     peak, peak_src = measured_peaks()
@@ -318,7 +353,9 @@ def run_ours(args):
             "metric": "registration pairs/sec (1024-pt, J=16)", "value": value, "unit": "pairs/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(B), "roofline": roofline, "em_step": em, "kernels": kernels,
+            "config": dict(workload_config(B), launch=("cuda_graph_replay (one two-stream step per graph)" if graphed is not None
+                                                         else "eager, two streams" if not args.no_overlap else "eager, one stream")),
+            "roofline": roofline, "em_step": em, "kernels": kernels,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": pipeline.launches_per_step(ITERS) * args.steps,
             "clocks": clocks, "eval_metrics_allreduced": metrics,
         }
@@ -333,6 +370,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of the CUDA-graph replay")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=256, help="pairs per GPU per step")
     ap.add_argument("--distinct", type=int, default=32, help="distinct synthetic pairs generated per rank (tiled to --pairs)")

@@ -96,6 +96,39 @@ def register_hot_path(src, tgt, src_feats, tgt_feats, src_o, tgt_o, n_clusters=1
             "tgt_node_feats": nf_t, "src_corr": corr}
 
 
+class GraphedHotPath:
+    """``register_hot_path`` over fixed device buffers, captured once into a CUDA graph and replayed.
+
+    A step is nine kernel launches, two memsets and a fork / join over two streams -- about 0.45 ms of host work
+    next to 1.4 ms of GPU work.  That margin is enough in a quiet process but not when the host hiccups (another
+    rank's Python on the same socket, an ``nvidia-smi`` poll holding a driver lock): the GPU then waits for
+    launches.  Replaying the captured step costs one launch and keeps the two-stream overlap exactly as captured.
+
+    The inputs are STATIC: write new pairs into the tensors passed here (``copy_``) and call ``replay()``; the
+    returned dict holds the same output tensors every time (clone what must outlive the next replay).
+    """
+
+    def __init__(self, src, tgt, src_feats, tgt_feats, src_o, tgt_o, n_clusters=16, k=20, iters=10, warmup=3):
+        self.inputs = (src, tgt, src_feats, tgt_feats, src_o, tgt_o)
+        self.args = (n_clusters, k, iters)
+        dev = src.device
+        cur = torch.cuda.current_stream(dev)
+        warm = torch.cuda.Stream(device=dev)
+        warm.wait_stream(cur)
+        with torch.cuda.stream(warm):                 # lazy one-time setup (function attributes, driver entry points)
+            for _ in range(max(int(warmup), 1)):
+                register_hot_path(*self.inputs, *self.args)
+        cur.wait_stream(warm)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = register_hot_path(*self.inputs, *self.args)
+
+    def replay(self):
+        self.graph.replay()
+        return self.out
+
+
 class _Stage:
     def __init__(self, timers, name):
         self.timers, self.name = timers, name
