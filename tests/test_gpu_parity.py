@@ -491,3 +491,73 @@ def test_graphed_hot_path_replays_the_eager_result(og):
         torch.cuda.synchronize()
         for name in ("rot", "trans", "src_gamma", "tgt_node_feats", "edge_src"):
             assert torch.equal(out[name], ref[name]), name
+
+
+# ------------------------------------------------------------------------------------------ edge cases
+def test_empty_batches_return_empty_results(og):
+    """B = 0 is legal everywhere on the path (a rank whose shard is empty): shapes are kept, nothing is launched."""
+    z = lambda *shape: torch.zeros(*shape, device="cuda")
+    idx, _, edge = og.ops.knn_graph(z(0, 64, 3), z(0, 64, 3), 8, want_edge=True)
+    assert tuple(idx.shape) == (0, 64, 8) and idx.dtype == torch.int64 and tuple(edge.shape) == (0, 64, 8, 6)
+    gam, pi, mu, _ = og.ops.sinkhorn_cluster(z(0, 64, 3), z(0, 64), 16)
+    assert tuple(gam.shape) == (0, 64, 16) and tuple(pi.shape) == (0, 16) and tuple(mu.shape) == (0, 16, 3)
+    pi, mu = og.ops.gmm_moments(z(0, 64, 16), z(0, 64, 32))
+    assert tuple(mu.shape) == (0, 16, 32)
+    rot, trans, corr, _ = og.ops.soft_procrustes(z(0, 16, 3), z(0, 16, 3), z(0, 16, 32), z(0, 16, 32), 0.05)
+    assert tuple(rot.shape) == (0, 3, 3)
+    torch.cuda.synchronize()
+
+
+def test_bad_arguments_raise_with_the_library_message(og):
+    """Errors come back as Python exceptions carrying the C library's own message (include/ogmm_b200.h: status codes
+    + ogmm_last_error); nothing falls back to another implementation."""
+    x = torch.rand(2, 16, 3, device="cuda")
+    with pytest.raises(og._lib.OgmmError, match="exceeds the number of candidates"):
+        og.ops.knn_graph(x, x, 17)
+    with pytest.raises(og._lib.OgmmError, match="EUNSUPPORTED"):
+        og.ops.knn_graph(torch.rand(1, 128, 3, device="cuda"), torch.rand(1, 128, 3, device="cuda"), 65)
+    with pytest.raises(ValueError):
+        og.ops.knn_graph(x, torch.rand(2, 16, 4, device="cuda"), 4)
+    with pytest.raises(TypeError, match="float32"):
+        og.ops.knn_graph(x.double(), x.double(), 4)
+    with pytest.raises(TypeError, match="CUDA"):
+        og.ops.knn_graph(x.cpu(), x.cpu(), 4)
+    with pytest.raises(ValueError):
+        og.ops.gmm_moments(torch.rand(2, 16, 4, device="cuda"), torch.rand(2, 15, 8, device="cuda"))
+    # the call after an error works (the error state is per thread and not sticky)
+    assert og.ops.knn_graph(x, x, 4)[0].shape == (2, 16, 4)
+
+
+def test_duplicate_points_resolve_to_the_lowest_indices(og, orc):
+    """Collisions: a cloud of identical points has all distances equal (the clamp floor), so every row must list the
+    k lowest indices in order; half-duplicated clouds must agree with the oracle's (distance, index) order."""
+    same = torch.full((2, 300, 3), 0.25, device="cuda")
+    idx = og.ops.knn_graph(same, same, 20)[0]
+    assert torch.equal(idx.cpu(), torch.arange(20).expand(2, 300, 20))
+    g = torch.Generator().manual_seed(9)
+    base = torch.rand(2, 150, 3, generator=g)
+    dup = torch.cat([base, base], 1)                               # every point twice: ties in every row
+    idx = og.ops.knn_graph(cu(dup), cu(dup), 12)[0].cpu()
+    ref = orc.knn_indices(dup, dup, 12)
+    d = orc.pairwise_sqdist(dup, dup)
+    assert torch.equal(torch.gather(d, 2, idx), torch.gather(d, 2, ref))          # same distances row by row
+    key = torch.gather(d, 2, idx)
+    tie = key[:, :, 1:] == key[:, :, :-1]
+    assert bool((idx[:, :, 1:][tie] > idx[:, :, :-1][tie]).all()), "ties must be listed by ascending index"
+
+
+def test_largest_supported_sizes(og, orc):
+    """Upper ends of the kernels' ranges: the 3-D sweep at 4096 points, k = 64, the clustering at 8192 points."""
+    g = torch.Generator().manual_seed(4)
+    x = torch.rand(1, 4096, 3, generator=g)
+    idx = og.ops.knn_graph(cu(x), cu(x), 64)[0].cpu()
+    ref = orc.knn_indices(x, x, 64)
+    rows, d64 = decidable_rows(x, x, 64)
+    assert rows.float().mean() > 0.2 and torch.equal(idx[rows], ref[rows])
+    # undecidable rows (fp32 near-ties somewhere among 64 gaps) still pick neighbours at the same distances
+    assert float((torch.gather(d64, 2, idx) - torch.gather(d64, 2, ref)).abs().max()) < 1e-6
+    xyz = torch.rand(1, 8192, 3, generator=g)
+    o = torch.sigmoid(torch.randn(1, 8192, generator=g))
+    gam, pi, mu, _ = og.ops.sinkhorn_cluster(cu(xyz), cu(o), 16)
+    rg, rpi, rmu, _ = orc.sinkhorn_kmeans(xyz, torch.zeros(1, 8192, 4), o, 16)
+    assert relerr(pi, rpi) < 1e-4 and float((mu.cpu() - rmu).abs().max()) < 1e-4
