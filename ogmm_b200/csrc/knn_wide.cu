@@ -115,6 +115,17 @@ __device__ __forceinline__ void load_tile_sw128(unsigned char* tile, int rows, c
     const int chunks = KB * 8;
     const int sh = 31 - __clz(chunks);
     const bool pow2 = (chunks & (chunks - 1)) == 0;
+    if (vec_ok && pow2 && C == 4 * chunks && row0 + rows <= n_valid) {
+        // full tile of contiguous, aligned rows: 16-byte cp.async straight into the swizzled layout, no registers
+        const uint32_t t0 = smem_u32(tile);
+        for (int e = threadIdx.x; e < rows * chunks; e += kWThreads) {
+            const int r = e >> sh, ch = e & (chunks - 1);
+            const float* p = base + (int64_t)(row0 + r) * sn + 4 * ch;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(t0 + (uint32_t)((ch >> 3) * rows * 128) + sw128_off(r, ch & 7)), "l"(p) : "memory");
+        }
+        asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+        return;
+    }
     for (int e = threadIdx.x; e < rows * chunks; e += kWThreads) {
         const int r = pow2 ? (e >> sh) : e / chunks;
         const int ch = e - r * chunks;
@@ -192,21 +203,11 @@ knn_wide_kernel(WideArgs a) {
     const uint32_t idesc = make_idesc_tf32(kWQ, BN);
     const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
     uint32_t parity = 0;
-    const float floor_d = a.normalize ? -INFINITY : 1e-12f;           // clamp(min=1e-12) of the non-cosine form
     const int col_lo = half * (BN / 2), col_hi = col_lo + BN / 2;
 
     // loads candidate tile m0 into sB / s_cn and runs the MMAs; on return the accumulators are in TMEM
     auto gram_tile = [&](int m0, bool track_max) {
         load_tile_sw128(sB, BN, db, a.d_sn, a.d_sc, m0, a.M, C, KB, d_vec);
-        __syncthreads();
-        for (int r = tid; r < BN; r += kWThreads) {
-            float cn = INFINITY;
-            if (m0 + r < a.M) {
-                cn = a.normalize ? 0.f : row_sqnorm_sw128(sB, BN, r, C);
-                if (track_max) atomicMax(s_cnmax, __float_as_int(cn));
-            }
-            s_cn[r] = cn;
-        }
         proxy_fence_async();
         __syncthreads();
         if (tid == 0) {
@@ -221,6 +222,16 @@ knn_wide_kernel(WideArgs a) {
             }
             umma_commit(s_bar);
         }
+        // candidate norms while the MMAs run (the selection needs them, the MMAs do not)
+        for (int r = tid; r < BN; r += kWThreads) {
+            float cn = INFINITY;
+            if (m0 + r < a.M) {
+                cn = a.normalize ? 0.f : row_sqnorm_sw128(sB, BN, r, C);
+                if (track_max) atomicMax(s_cnmax, __float_as_int(cn));
+            }
+            s_cn[r] = cn;
+        }
+        __syncthreads();
         mbar_wait(s_bar, parity);
         parity ^= 1;
         tc_fence_after();
@@ -243,11 +254,7 @@ knn_wide_kernel(WideArgs a) {
                 const float4 cn4 = *reinterpret_cast<const float4*>(s_cn + c0 + 4 * i4);
                 const float cnv[4] = {cn4.x, cn4.y, cn4.z, cn4.w};
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    float v = fmaf(-2.f, dot[4 * i4 + u], qn) + cnv[u];
-                    v = fmaxf(v, floor_d);
-                    vl.offer(v);
-                }
+                for (int u = 0; u < 4; ++u) vl.offer(fmaf(-2.f, dot[4 * i4 + u], cnv[u]));   // approx distance - |q|^2, unclamped
                 if (i4 & 1) vl.maybe_merge();
             }
         }
@@ -274,7 +281,10 @@ knn_wide_kernel(WideArgs a) {
     __syncthreads();                                                    // s_lists (= s_coll) is reused below
     // error bound of the approximate distance: 2 |dot_tf32 - dot| <= 2^-8 |x||y|, plus fp32 rounding slack
     const float xn = a.normalize ? 1.0f : qn, yn = a.normalize ? 1.0f : cn_max;
-    const float err = 0.00390625f * sqrtf(xn * yn) + 4e-6f * (xn + yn) + 1e-30f;
+    // Both passes compare v' = -2 dot + |y|^2 (the approximate distance minus |q|^2, without the clamp at 1e-12: a
+    // constant shift per query and a floor that only ever raises values, both harmless for a superset test; the
+    // floor's 1e-12 goes into the slack).  tau is the K-th smallest v'.
+    const float err = 0.00390625f * sqrtf(xn * yn) + 4e-6f * (xn + yn) + 2e-12f;
     // finite even when fewer than K candidates exist, and -inf for padding query rows: they never collect
     const float thr_b = valid ? fminf(tau + 2.f * err, 3.0e38f) : -INFINITY;
 
@@ -306,8 +316,7 @@ knn_wide_kernel(WideArgs a) {
                 const float cnv[4] = {cn4.x, cn4.y, cn4.z, cn4.w};
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    float v = fmaf(-2.f, dot[4 * i4 + u], qn) + cnv[u];
-                    v = fmaxf(v, floor_d);
+                    const float v = fmaf(-2.f, dot[4 * i4 + u], cnv[u]);
                     if (v <= thr_b) {                                   // padding columns carry +inf, thr_b is finite
                         s_coll[(half * cap2 + ncoll) * kWQ + ql] = m0 + c0 + 4 * i4 + u;
                         if (++ncoll == cap2) { drain(); ++drains; }
