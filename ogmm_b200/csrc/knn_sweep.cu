@@ -100,6 +100,77 @@ __device__ __forceinline__ void bitonic_sort_pairs(float* key, int* val, int n) 
     }
 }
 
+// The same sort for n = 256 * E with E elements per thread held in registers: compare-exchange distances below E
+// stay inside the thread, distances below 32 E go through warp shuffles, and only the log2(8) (log2(8) + 1) / 2 = 6
+// cross-warp stages per sort touch shared memory and the block barrier (the shared-memory version above pays a
+// barrier in every one of its 55 stages at n = 1024, which made the sort ~30 % of the sweep kernel's warp time).
+// Fully unrolled: every register index is a compile-time constant.
+template <int E>
+__device__ __forceinline__ void bitonic_sort_pairs_regs(float* key, int* val) {
+    constexpr int n = kSwThreads * E;
+    const int t = threadIdx.x;
+    float kr[E];
+    int vr[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) { kr[e] = key[t * E + e]; vr[e] = val[t * E + e]; }
+    __syncthreads();                                   // the arrays become the exchange scratch ([e][thread] layout)
+#pragma unroll
+    for (int k = 2; k <= n; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j < E) {
+                // partner inside the thread: elements e and e | j
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    if ((e & j) == 0) {
+                        const int f = e | j;
+                        const bool up = (k < E) ? ((e & k) == 0) : (((t * E) & k) == 0);
+                        const bool gt = (kr[e] > kr[f]) || (kr[e] == kr[f] && vr[e] > vr[f]);
+                        if (gt == up) {
+                            const float tk = kr[e]; kr[e] = kr[f]; kr[f] = tk;
+                            const int tv = vr[e]; vr[e] = vr[f]; vr[f] = tv;
+                        }
+                    }
+                }
+            } else {
+                const int pt = j / E;                  // partner thread = t ^ pt, same e
+                const bool lower = (t & pt) == 0;
+                const bool up = ((t * E) & k) == 0;    // k > j >= E: the direction bit lies in the thread index
+                const bool take_min = lower == up;
+                if (pt >= 32) {
+#pragma unroll
+                    for (int e = 0; e < E; ++e) { key[e * kSwThreads + t] = kr[e]; val[e * kSwThreads + t] = vr[e]; }
+                    __syncthreads();
+                }
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    float ok;
+                    int ov;
+                    if (pt >= 32) { ok = key[e * kSwThreads + (t ^ pt)]; ov = val[e * kSwThreads + (t ^ pt)]; }
+                    else { ok = __shfl_xor_sync(kFull, kr[e], pt); ov = __shfl_xor_sync(kFull, vr[e], pt); }
+                    const bool gt = (kr[e] > ok) || (kr[e] == ok && vr[e] > ov);      // mine after the partner's
+                    if (gt == take_min) { kr[e] = ok; vr[e] = ov; }
+                }
+                if (pt >= 32) __syncthreads();
+            }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < E; ++e) { key[t * E + e] = kr[e]; val[t * E + e] = vr[e]; }
+    __syncthreads();
+}
+
+// dispatch: register version for the sizes the sweep kernel meets (256 .. 4096 points), generic otherwise
+__device__ __forceinline__ void sort_pairs(float* key, int* val, int n) {
+    switch (n) {
+        case 256:  bitonic_sort_pairs_regs<1>(key, val); break;
+        case 512:  bitonic_sort_pairs_regs<2>(key, val); break;
+        case 1024: bitonic_sort_pairs_regs<4>(key, val); break;
+        case 2048: bitonic_sort_pairs_regs<8>(key, val); break;
+        default:   bitonic_sort_pairs(key, val, n); break;
+    }
+}
+
 __device__ __forceinline__ float sqn3(float x, float y, float z) {
     return __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
 }
@@ -176,8 +247,8 @@ knn3_sweep_kernel(const float* __restrict__ src, int64_t s_sb, int64_t s_sn, int
             s_qord[n] = n < N ? n : 0x7fffffff;
         }
     __syncthreads();
-    bitonic_sort_pairs(s_ckey, s_cord, Mp);
-    if (!self) bitonic_sort_pairs(s_qkey, s_qord, Np);
+    sort_pairs(s_ckey, s_cord, Mp);
+    if (!self) sort_pairs(s_qkey, s_qord, Np);
     for (int m = tid; m < M; m += kSwThreads) {
         const float* p = db + (int64_t)s_cord[m] * d_sn;
         const float x = p[0], y = p[d_sc], z = p[2 * d_sc];

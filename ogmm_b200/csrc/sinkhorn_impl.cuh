@@ -554,8 +554,8 @@ __device__ __forceinline__ void process_cloud(const SinkhornParams& P, const Sme
 #pragma unroll
                     for (int w = 0; w < NW; ++w) sj += S.wtot[w * JF + j];
                     const bool live = j < J;
-                    const float bn = live ? __fdiv_rn(S.logq[j], sj) : 0.f;
-                    const float vn = live ? P.eps * __logf(bn) : 0.f;
+                    const float bn = live ? S.logq[j] * fast_rcp(sj) : 0.f;
+                    const float vn = live ? eps_ln2 * fast_lg2(bn) : 0.f;
                     float dv = (live && lane < 16) ? fabsf(vn - S.v[j]) : 0.f;
                     bool ok = !live || (sj > 1e-30f && sj < 1e30f);
                     float bmax = live ? bn : 0.f, bmin = live ? bn : INFINITY;
