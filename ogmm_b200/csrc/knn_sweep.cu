@@ -57,15 +57,26 @@ struct TopK64 {
     // Sorted insert: strict compare up to the insertion point, then every entry shifts down by one.
     // (A dependency-free variant -- all compares first, then independent selects -- measured 10 % slower:
     // this kernel is bound by instruction count, not by the carried chain.)
-    __device__ __forceinline__ void insert(u64 kv) {
+    template <int A>
+    __device__ __forceinline__ void insert_from(u64 kv) {      // positions A .. K-1; the caller knows kv >= key[A-1]
         bool moved = false;
 #pragma unroll
-        for (int j = 0; j < K; ++j) {
+        for (int j = A; j < K; ++j) {
             moved = moved || (kv < key[j]);
             const u64 t = key[j];
             key[j] = moved ? kv : t;
             kv = moved ? t : kv;
         }
+    }
+    // Candidates met late in the sweep barely beat the threshold, so they land near the tail of the list: when no
+    // lane of the warp lands in the first half (or three quarters), only the tail is shifted.
+    __device__ __forceinline__ void insert(u64 kv) {
+        if constexpr (K >= 16) {
+            constexpr int Q3 = (3 * K) / 4, Q2 = K / 2;
+            if (!__any_sync(kFull, kv < key[Q3 - 1])) { insert_from<Q3>(kv); return; }
+            if (!__any_sync(kFull, kv < key[Q2 - 1])) { insert_from<Q2>(kv); return; }
+        }
+        insert_from<0>(kv);
     }
     __device__ __forceinline__ void merge() {
         const int most = __reduce_max_sync(kFull, cnt);
