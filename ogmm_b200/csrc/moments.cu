@@ -432,6 +432,99 @@ softmax_moments_kernel(const float* __restrict__ logits, const float* __restrict
     }
 }
 
+// J <= 16 variant (DeepGMR's J = 16): thread per point with all J softmax terms in registers, the four moment sums
+// of a cluster accumulated per thread over its points and folded ONCE per pass with the 16-column butterfly (64 + 16
+// shuffles per thread instead of 80 per point and cluster), one reciprocal per point, MUFU exponentials.  The generic
+// kernel above stays for J > 16.
+__global__ void __launch_bounds__(kSoftThreads, 2)
+softmax_moments16_kernel(const float* __restrict__ logits, const float* __restrict__ pts, int64_t p_sb, int64_t p_sn,
+                         int64_t p_sd, int N, int J, float* __restrict__ gamma_out, float* __restrict__ pi_out,
+                         float* __restrict__ mu_out, float* __restrict__ sigma_out) {
+    constexpr int NW = kSoftThreads / 32;
+    __shared__ float s_w[NW][kJC][4];
+    __shared__ float s_mu[kJC][4];                   // mu xyz, npi
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* lg = logits + (int64_t)b * J * N;
+    const float* x = pts + (int64_t)b * p_sb;
+    const int col = (lane >> 1) & 15;
+
+    // softmax row of point n in registers: e[j] = exp(l_j - max) / sum, zero for j >= J
+    auto softmax_row = [&](int n, float (&e)[kJC]) {
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < kJC; ++j) { e[j] = j < J ? __ldg(lg + (int64_t)j * N + n) : -INFINITY; mx = fmaxf(mx, e[j]); }
+        float den = 0.f;
+#pragma unroll
+        for (int j = 0; j < kJC; ++j) { e[j] = __expf(e[j] - mx); den += e[j]; }      // exp(-inf) = 0 for the padding
+        const float inv = __fdiv_rn(1.0f, den);
+#pragma unroll
+        for (int j = 0; j < kJC; ++j) e[j] *= inv;
+    };
+
+    float a0[kJC], ax[kJC], ay[kJC], az[kJC];
+#pragma unroll
+    for (int j = 0; j < kJC; ++j) { a0[j] = 0.f; ax[j] = 0.f; ay[j] = 0.f; az[j] = 0.f; }
+    for (int n = tid; n < N; n += kSoftThreads) {
+        const float px = x[(int64_t)n * p_sn], py = x[(int64_t)n * p_sn + p_sd], pz = x[(int64_t)n * p_sn + 2 * p_sd];
+        float e[kJC];
+        softmax_row(n, e);
+#pragma unroll
+        for (int j = 0; j < kJC; ++j) {
+            if (gamma_out && j < J) gamma_out[((int64_t)b * J + j) * N + n] = e[j];
+            a0[j] += e[j];
+            ax[j] = fmaf(e[j], px, ax[j]); ay[j] = fmaf(e[j], py, ay[j]); az[j] = fmaf(e[j], pz, az[j]);
+        }
+    }
+    {
+        const float t0 = butterfly16(a0, lane), tx = butterfly16(ax, lane), ty = butterfly16(ay, lane), tz = butterfly16(az, lane);
+        if ((lane & 1) == 0) { s_w[warp][col][0] = t0; s_w[warp][col][1] = tx; s_w[warp][col][2] = ty; s_w[warp][col][3] = tz; }
+    }
+    __syncthreads();
+    if (tid < J) {
+        float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) { t0 += s_w[w][tid][0]; t1 += s_w[w][tid][1]; t2 += s_w[w][tid][2]; t3 += s_w[w][tid][3]; }
+        const float pi = __fdiv_rn(t0, (float)N);
+        const float npi = __fadd_rn(__fmul_rn(pi, (float)N), 1e-5f);
+        pi_out[(int64_t)b * J + tid] = pi;
+        const float m0 = __fdiv_rn(t1, npi), m1 = __fdiv_rn(t2, npi), m2 = __fdiv_rn(t3, npi);
+        s_mu[tid][0] = m0; s_mu[tid][1] = m1; s_mu[tid][2] = m2; s_mu[tid][3] = npi;
+        float* m = mu_out + ((int64_t)b * J + tid) * 3;
+        m[0] = m0; m[1] = m1; m[2] = m2;
+    }
+    if (!sigma_out) return;
+    __syncthreads();
+    // ---- sigma_j = sum_n gamma_nj |x_n - mu_j|^2 / npi_j: the softmax rows are recomputed (logits are L2-resident)
+    float s2[kJC];
+#pragma unroll
+    for (int j = 0; j < kJC; ++j) s2[j] = 0.f;
+    for (int n = tid; n < N; n += kSoftThreads) {
+        const float px = x[(int64_t)n * p_sn], py = x[(int64_t)n * p_sn + p_sd], pz = x[(int64_t)n * p_sn + 2 * p_sd];
+        float e[kJC];
+        softmax_row(n, e);
+#pragma unroll
+        for (int j = 0; j < kJC; ++j) {
+            if (j < J) {
+                const float dx = px - s_mu[j][0], dy = py - s_mu[j][1], dz = pz - s_mu[j][2];
+                s2[j] = fmaf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)), e[j], s2[j]);
+            }
+        }
+    }
+    {
+        const float t = butterfly16(s2, lane);
+        if ((lane & 1) == 0) s_w[warp][col][0] = t;
+    }
+    __syncthreads();
+    if (tid < J) {
+        float t0 = 0.f;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) t0 += s_w[w][tid][0];
+        const float sg = __fdiv_rn(t0, s_mu[tid][3]);
+        float* so = sigma_out + ((int64_t)b * J + tid) * 9;
+        so[0] = sg; so[1] = 0.f; so[2] = 0.f; so[3] = 0.f; so[4] = sg; so[5] = 0.f; so[6] = 0.f; so[7] = 0.f; so[8] = sg;
+    }
+}
+
 }  // namespace ogmm
 
 using namespace ogmm;
@@ -533,6 +626,12 @@ extern "C" __attribute__((visibility("default"))) int ogmm_softmax_moments(const
     OGMM_REQUIRE(J <= 1024, OGMM_EUNSUPPORTED, "ogmm_softmax_moments: J=%lld > 1024", (long long)J);
     if (B == 0) return OGMM_OK;
     OGMM_REQUIRE(logits && pts && pi_out && mu_out, OGMM_EINVAL, "ogmm_softmax_moments: null pointer");
+    if (J <= kJC) {
+        softmax_moments16_kernel<<<(unsigned)B, kSoftThreads, 0, as_stream(stream)>>>(
+            logits, pts, p_sb, p_sn, p_sd, (int)N, (int)J, gamma_out, pi_out, mu_out, sigma_out);
+        OGMM_LAUNCH_CHECK("softmax_moments16_kernel");
+        return OGMM_OK;
+    }
     const size_t smem = sizeof(float) * ((size_t)(kSoftThreads / 32) * J * 4 + (size_t)J * 4);
     if (smem > 48 * 1024) {
         int st = cuda_status(cudaFuncSetAttribute(softmax_moments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -238,6 +238,21 @@ def test_feature_moments_tensor_opt_in(og, orc, n, d, monkeypatch):
     assert float(((mu.cpu().double() - rmu).abs() / rmu.abs().clamp(min=1e-3)).max()) < 1e-4
 
 
+@pytest.mark.parametrize("b,n,j", [(3, 1024, 16), (2, 700, 16), (2, 1024, 8), (2, 333, 5), (2, 1024, 24), (1, 4096, 16)])
+def test_deepgmr_em_vs_oracle(og, orc, b, n, j):
+    """DeepGMR's fused E-step + M-step + sigma (J <= 16: register-resident softmax rows; J > 16: the generic kernel)
+    against the FP64 oracle, ragged point counts and cluster counts below the 16-column padding included."""
+    from ogmm_b200 import synth
+    src, _, _, _ = synth.icl_nuim_batch(5, b, n)
+    pts = torch.from_numpy(src)                                   # (B,3,N), metres
+    g = torch.Generator().manual_seed(n + j)
+    logits = torch.randn(b, j, n, generator=g) * 4
+    rg, rpi, rmu, rsg = orc.deepgmr_em(logits.double(), pts.double())
+    gam, pi, mu, sigma = og.deepgmr_em(cu(logits), cu(pts))
+    assert float((gam.cpu().double() - rg).abs().max()) < 2e-6
+    assert relerr(pi, rpi) < 1e-5 and relerr(mu, rmu) < 1e-5 and relerr(sigma, rsg) < 1e-4
+
+
 def test_deepgmr_em_and_register(og, golden):
     g = golden("deepgmr")
     gam, pi, mu, sigma = og.deepgmr_em(cu(g["src_logits"]), cu(g["src"]))
