@@ -281,28 +281,62 @@ knn_generic_kernel(const float* __restrict__ src, int64_t s_sb, int64_t s_sn, in
 }
 
 // ---------------------------------------------------------------------------------------------------
-// edge gather: out[b][n][kk][0:C] = x[:, idx] - x[:, n]; out[..][C:2C] = x[:, n].  One thread per
-// (b, n, kk, c) element pair, consecutive threads write consecutive floats.
+// edge gather: out[b][n][kk][0:C] = x[:, idx] - x[:, n]; out[..][C:2C] = x[:, n].
+// Two kernels, both one cloud per blockIdx.y with 32-bit index arithmetic inside the cloud:
+//   C <= 4 (xyz, the DGCNN first layer): one thread per (n, kk) row -- idx and the centre are read once per row,
+//     the 2C floats are written as 8-byte pairs; a warp covers 32 consecutive rows = one contiguous span.
+//   any C: one thread per output element, consecutive threads write consecutive floats.
+template <int C>
+__global__ void __launch_bounds__(256)
+edge_gather_rows_kernel(const float* __restrict__ x, int64_t sb, int64_t sc, int64_t sn, const int64_t* __restrict__ idx,
+                        int N, int k, float* __restrict__ out) {
+    // the CTA's 256 rows are one contiguous span of 256 * 2C floats: staged in shared memory (row pitch 2C + 1 keeps
+    // the per-thread writes conflict-free) and written back with consecutive threads on consecutive floats
+    __shared__ float s_out[256 * (2 * C + 1)];
+    const int rows = N * k;
+    const int r0 = blockIdx.x * blockDim.x, r = r0 + threadIdx.x;
+    const int b = blockIdx.y;
+    if (r < rows) {
+        const int n = r / k;
+        const float* xb = x + (int64_t)b * sb;
+        int64_t j = idx[(int64_t)b * rows + r];
+        j = j < 0 ? 0 : (j >= N ? N - 1 : j);
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const float ctr = __ldg(xb + (int64_t)c * sc + (int64_t)n * sn);
+            s_out[threadIdx.x * (2 * C + 1) + c] = __ldg(xb + (int64_t)c * sc + j * sn) - ctr;
+            s_out[threadIdx.x * (2 * C + 1) + C + c] = ctr;
+        }
+    }
+    __syncthreads();
+    const int n_rows = min(256, rows - r0);
+    float* o = out + ((int64_t)b * rows + r0) * (2 * C);
+    for (int e = threadIdx.x; e < n_rows * 2 * C; e += 256) {
+        const int rr = e / (2 * C), cc = e - rr * (2 * C);
+        o[e] = s_out[rr * (2 * C + 1) + cc];
+    }
+}
+
 __global__ void __launch_bounds__(256)
 edge_gather_kernel(const float* __restrict__ x, int64_t sb, int64_t sc, int64_t sn, const int64_t* __restrict__ idx,
-                   int64_t total, int C, int N, int k, float* __restrict__ out) {
-    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= total) return;
-    const int c2 = (int)(e % (2 * C));
-    const int64_t row = e / (2 * C);          // (b, n, kk)
-    const int64_t bn = row / k;
-    const int n = (int)(bn % N);
-    const int64_t b = bn / N;
-    const float* xb = x + b * sb;
-    const int c = c2 < C ? c2 : c2 - C;
-    const float ctr = xb[(int64_t)c * sc + (int64_t)n * sn];
+                   int C, int N, int k, float* __restrict__ out) {
+    const unsigned per_cloud = (unsigned)N * (unsigned)k * 2u * (unsigned)C;
+    const unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= per_cloud) return;
+    const int b = blockIdx.y;
+    const unsigned c2 = e % (2u * C);
+    const unsigned row = e / (2u * C);        // (n, kk)
+    const unsigned n = row / (unsigned)k;
+    const float* xb = x + (int64_t)b * sb;
+    const unsigned c = c2 < (unsigned)C ? c2 : c2 - C;
+    const float ctr = __ldg(xb + (int64_t)c * sc + (int64_t)n * sn);
     float v = ctr;
-    if (c2 < C) {
-        int64_t j = idx[row];
+    if (c2 < (unsigned)C) {
+        int64_t j = idx[(int64_t)b * N * k + row];
         j = j < 0 ? 0 : (j >= N ? N - 1 : j);
-        v = xb[(int64_t)c * sc + j * sn] - ctr;
+        v = __ldg(xb + (int64_t)c * sc + j * sn) - ctr;
     }
-    out[e] = v;
+    out[(int64_t)b * per_cloud + e] = v;
 }
 
 }  // namespace ogmm
@@ -385,11 +419,20 @@ extern "C" __attribute__((visibility("default"))) int ogmm_edge_gather(const flo
                  OGMM_EINVAL, "ogmm_edge_gather: bad sizes");
     if (B == 0) return OGMM_OK;
     OGMM_REQUIRE(x && idx && edge_out, OGMM_EINVAL, "ogmm_edge_gather: null pointer");
-    const int64_t total = B * N * k * 2 * C;
-    const int64_t blocks = (total + 255) / 256;
-    OGMM_REQUIRE(blocks < (1ll << 31), OGMM_EUNSUPPORTED, "ogmm_edge_gather: output too large");
-    edge_gather_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(x, sb, sc, sn, idx, total, (int)C, (int)N,
-                                                                        (int)k, edge_out);
+    OGMM_REQUIRE(B < 65536 && N * k * 2 * C < (1ll << 31), OGMM_EUNSUPPORTED, "ogmm_edge_gather: a cloud's edge tensor exceeds 2^31 elements");
+    cudaStream_t s = as_stream(stream);
+    if (C <= 4) {
+        dim3 grid((unsigned)((N * k + 255) / 256), (unsigned)B);
+        switch (C) {
+            case 1: edge_gather_rows_kernel<1><<<grid, 256, 0, s>>>(x, sb, sc, sn, idx, (int)N, (int)k, edge_out); break;
+            case 2: edge_gather_rows_kernel<2><<<grid, 256, 0, s>>>(x, sb, sc, sn, idx, (int)N, (int)k, edge_out); break;
+            case 3: edge_gather_rows_kernel<3><<<grid, 256, 0, s>>>(x, sb, sc, sn, idx, (int)N, (int)k, edge_out); break;
+            default: edge_gather_rows_kernel<4><<<grid, 256, 0, s>>>(x, sb, sc, sn, idx, (int)N, (int)k, edge_out); break;
+        }
+    } else {
+        dim3 grid((unsigned)((N * k * 2 * C + 255) / 256), (unsigned)B);
+        edge_gather_kernel<<<grid, 256, 0, s>>>(x, sb, sc, sn, idx, (int)C, (int)N, (int)k, edge_out);
+    }
     OGMM_LAUNCH_CHECK("edge_gather_kernel");
     return OGMM_OK;
 }
