@@ -285,18 +285,20 @@ int ogmm_launch_moments_feat_tma(const float* gamma, int64_t g_sb, int64_t g_sn,
     EncodeTiledFn encode = encode_tiled_fn();
     if (!encode) return OGMM_EUNSUPPORTED;
 
-    static bool configured = false;
-    static int sm_count = 0;
-    if (!configured) {
-        int st = cuda_status(cudaFuncSetAttribute(gmm_moments_feat_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                  kTmSmemPerCta), "cudaFuncSetAttribute(gmm_moments_feat_tma_kernel)");
-        if (st != OGMM_OK) return st;
-        int dev = 0;
-        st = cuda_status(cudaGetDevice(&dev), "cudaGetDevice");
-        if (st != OGMM_OK) return st;
+    // per device (one process may drive several GPUs from several threads, e.g. nn.DataParallel): the function attribute
+    // belongs to the current device's context, so it is set on every call; the SM count is cached per device
+    static int sm_count_by_dev[64] = {0};
+    int dev = 0;
+    int st = cuda_status(cudaGetDevice(&dev), "cudaGetDevice");
+    if (st != OGMM_OK) return st;
+    st = cuda_status(cudaFuncSetAttribute(gmm_moments_feat_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmSmemPerCta),
+                     "cudaFuncSetAttribute(gmm_moments_feat_tma_kernel)");
+    if (st != OGMM_OK) return st;
+    int sm_count = (dev >= 0 && dev < 64) ? sm_count_by_dev[dev] : 0;
+    if (sm_count == 0) {
         st = cuda_status(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev), "cudaDeviceGetAttribute");
         if (st != OGMM_OK) return st;
-        configured = true;
+        if (dev >= 0 && dev < 64) sm_count_by_dev[dev] = sm_count;
     }
     const int64_t resident = 2ll * sm_count;         // two CTAs per SM (shared memory and registers)
 

@@ -576,3 +576,36 @@ def test_largest_supported_sizes(og, orc):
     gam, pi, mu, _ = og.ops.sinkhorn_cluster(cu(xyz), cu(o), 16)
     rg, rpi, rmu, _ = orc.sinkhorn_kmeans(xyz, torch.zeros(1, 8192, 4), o, 16)
     assert relerr(pi, rpi) < 1e-4 and float((mu.cpu() - rmu).abs().max()) < 1e-4
+
+
+def test_two_devices_from_two_threads_like_dataparallel(og):
+    """nn.DataParallel (train.py:191) runs the forward from one Python thread per device in ONE process: the library must
+    launch on the caller's current device and keep no per-process kernel configuration.  Needs two GPUs."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    import threading
+    from ogmm_b200 import pipeline, synth
+    h = synth.hot_path_inputs(0, 8, 1024, 128)
+    keys = ("src", "tgt", "src_feats", "tgt_feats", "src_o", "tgt_o")
+    host = {k: torch.from_numpy(np.ascontiguousarray(h[k])).float() for k in keys}
+    out, err = {}, []
+
+    def work(dev):
+        try:
+            with torch.cuda.device(dev):
+                d = {k: v.to(f"cuda:{dev}") for k, v in host.items()}
+                for _ in range(3):
+                    r = pipeline.register_hot_path(*(d[k] for k in keys), 16, 20)
+                torch.cuda.synchronize(dev)
+                out[dev] = (r["rot"].cpu(), r["trans"].cpu(), r["src_node_feats"].cpu())
+        except Exception as e:                                    # surfaced in the main thread below
+            err.append(e)
+
+    threads = [threading.Thread(target=work, args=(dev,)) for dev in (0, 1)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not err, err
+    for a, b in zip(out[0], out[1]):
+        assert torch.equal(a, b)
