@@ -125,7 +125,11 @@ int ogmm_sinkhorn(const float* cost, const float* p, const float* q, int64_t B, 
  *   pi_out (B,J); mu_out (B,J,D); sigma_out (optional) (B,J,D,D) = (sum gamma|x-mu|^2/npi) I.
  * ogmm_gmm_moments is the small-D kernel (D <= 16, e.g. xyz, with optional sigma);
  * ogmm_gmm_moments_feat is the streaming kernel for wide features in their native (B,D,N)
- * layout (pass strides accordingly), reading every feature value from HBM exactly once. */
+ * layout (pass strides accordingly), reading every feature value from HBM exactly once.
+ *   J == 16, N % 4 == 0, unit point stride, 16-byte aligned rows, contiguous gamma: persistent
+ *   TMA -> shared memory -> mma.sync 3xTF32 pipeline (FP32-grade accuracy, 1.4e-6 relative).
+ *   Any other shape or stride: FP32 FFMA2 kernel.  Environment switches for A/B timing:
+ *   OGMM_FEAT_NO_TMA=1 forces the FP32 kernel, OGMM_FEAT_TENSOR=1 selects the tcgen05 variant. */
 int ogmm_gmm_moments(const float* gamma, int64_t g_sb, int64_t g_sn, int64_t g_sj,
                      const float* pts, int64_t p_sb, int64_t p_sn, int64_t p_sd,
                      int64_t B, int64_t N, int64_t J, int64_t D,
