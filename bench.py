@@ -214,8 +214,19 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # stdout carries the one JSON line only
-        dist.init_process_group("nccl", device_id=dev)
+        # stdout carries the one JSON line only: NCCL prints its version banner with a bare printf when the communicator
+        # is created, so file descriptor 1 points at stderr while that happens
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     og._lib.load()
     B = args.pairs
 
