@@ -101,6 +101,66 @@ __host__ __device__ inline size_t soft_procrustes_smem(int Js, int Jt) {
     return sizeof(float) * ((size_t)Js * Jt + (size_t)(Js + Jt) * kDTP + (Js + Jt) + 3 * (size_t)Js + Js + 3 * (size_t)(Js + Jt) + 32);
 }
 
+// Steps 3-5 of GMMSVD shared by both similarity kernels: softmax(sim / T) rows, soft correspondences, weights,
+// weighted Procrustes over the Js components.  `sim` holds the cosine similarities on entry (all threads synchronised).
+__device__ __forceinline__ void soft_head_tail(float* sim, float* corr, float* wgt, const float* mus, const float* mut,
+                                               int Js, int Jt, float temperature, int b, float* __restrict__ rot_out,
+                                               float* __restrict__ trans_out, float* __restrict__ corr_out) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = kSPThreads / 32;
+    // 3+4. per source row: softmax(sim / T) over j, soft correspondence, weight
+    for (int i = warp; i < Js; i += NW) {
+        float* row = sim + (size_t)i * Jt;
+        float m = -INFINITY;
+        for (int j = lane; j < Jt; j += 32) { float z = __fdiv_rn(row[j], temperature); row[j] = z; m = fmaxf(m, z); }
+        m = warp_max(m);
+        float sum = 0.f;
+        for (int j = lane; j < Jt; j += 32) { float e = expf(row[j] - m); row[j] = e; sum += e; }
+        sum = warp_sum(sum);
+        float c0 = 0.f, c1 = 0.f, c2 = 0.f, w = 0.f;
+        for (int j = lane; j < Jt; j += 32) {
+            float sc = row[j] / sum;
+            w += sc;
+            c0 = fmaf(mut[3 * j], sc, c0); c1 = fmaf(mut[3 * j + 1], sc, c1); c2 = fmaf(mut[3 * j + 2], sc, c2);
+        }
+        c0 = warp_sum(c0); c1 = warp_sum(c1); c2 = warp_sum(c2); w = warp_sum(w);
+        if (lane == 0) { corr[i] = c0; corr[Js + i] = c1; corr[2 * Js + i] = c2; wgt[i] = w; }
+    }
+    __syncthreads();
+    for (int e = tid; e < 3 * Js; e += kSPThreads) corr_out[(int64_t)b * 3 * Js + e] = corr[e];
+
+    // 5. weighted Procrustes over the Js components (warp 0)
+    if (warp == 0) {
+        float sw = 0.f, ss[3] = {0.f, 0.f, 0.f}, sc[3] = {0.f, 0.f, 0.f};
+        for (int i = lane; i < Js; i += 32) {
+            float wi = wgt[i];
+            sw += wi;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { ss[a] += mus[3 * i + a] * wi; sc[a] += corr[a * Js + i] * wi; }
+        }
+        sw = warp_sum(sw);
+        float cs[3], ct[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { cs[a] = warp_sum(ss[a]) / sw; ct[a] = warp_sum(sc[a]) / sw; }
+        float cov[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) cov[i] = 0.f;
+        for (int i = lane; i < Js; i += 32) {
+            float wi = wgt[i];
+            float sa[3], cb[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { sa[a] = (mus[3 * i + a] - cs[a]) * wi; cb[a] = corr[a * Js + i] - ct[a]; }
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) cov[3 * a + c] += sa[a] * cb[c];
+        }
+#pragma unroll
+        for (int i = 0; i < 9; ++i) cov[i] = warp_sum(cov[i]);
+        if (lane == 0) finish_procrustes(cov, cs, ct, rot_out + (int64_t)b * 9, trans_out + (int64_t)b * 3);
+    }
+}
+
 __global__ void __launch_bounds__(kSPThreads)
 soft_procrustes_kernel(const float* __restrict__ src_mu, const float* __restrict__ tgt_mu,
                        const float* __restrict__ src_desc, const float* __restrict__ tgt_desc,
@@ -183,57 +243,83 @@ soft_procrustes_kernel(const float* __restrict__ src_mu, const float* __restrict
     if (head == 0) return;      // cos_similarity only
     __syncthreads();
 
-    // 3+4. per source row: softmax(sim / T) over j, soft correspondence, weight
-    for (int i = warp; i < Js; i += NW) {
-        float* row = sim + (size_t)i * Jt;
-        float m = -INFINITY;
-        for (int j = lane; j < Jt; j += 32) { float z = __fdiv_rn(row[j], temperature); row[j] = z; m = fmaxf(m, z); }
-        m = warp_max(m);
-        float sum = 0.f;
-        for (int j = lane; j < Jt; j += 32) { float e = expf(row[j] - m); row[j] = e; sum += e; }
-        sum = warp_sum(sum);
-        float c0 = 0.f, c1 = 0.f, c2 = 0.f, w = 0.f;
-        for (int j = lane; j < Jt; j += 32) {
-            float sc = row[j] / sum;
-            w += sc;
-            c0 = fmaf(mut[3 * j], sc, c0); c1 = fmaf(mut[3 * j + 1], sc, c1); c2 = fmaf(mut[3 * j + 2], sc, c2);
-        }
-        c0 = warp_sum(c0); c1 = warp_sum(c1); c2 = warp_sum(c2); w = warp_sum(w);
-        if (lane == 0) { corr[i] = c0; corr[Js + i] = c1; corr[2 * Js + i] = c2; wgt[i] = w; }
+    soft_head_tail(sim, corr, wgt, mus, mut, Js, Jt, temperature, b, rot_out, trans_out, corr_out);
+}
+
+// Same head with BOTH descriptor sets resident in shared memory ((Js + Jt) x (D + 4) floats; 66 KB at J = 16, D = 512):
+// one load phase with every byte in flight at once instead of D / 64 load -> barrier -> compute rounds, whose exposed
+// global-memory latency made the chunked kernel 43 us for 256 pairs.  Same arithmetic in the same order (row norm,
+// x / max(|x|, 1e-12) per element, one FMA chain over d ascending), so the results are bit-identical.
+__host__ __device__ inline size_t soft_procrustes_full_smem(int Js, int Jt, int D) {
+    return sizeof(float) * ((size_t)Js * Jt + (size_t)(Js + Jt) * (D + 4) + (Js + Jt) + 3 * (size_t)Js + Js + 3 * (size_t)(Js + Jt) + 32);
+}
+
+__global__ void __launch_bounds__(kSPThreads)
+soft_procrustes_full_kernel(const float* __restrict__ src_mu, const float* __restrict__ tgt_mu,
+                            const float* __restrict__ src_desc, const float* __restrict__ tgt_desc,
+                            int Js, int Jt, int D, float temperature,
+                            float* __restrict__ rot_out, float* __restrict__ trans_out,
+                            float* __restrict__ corr_out, float* __restrict__ sim_out, int head) {
+    extern __shared__ __align__(16) float smem[];
+    const int P = D + 4;                               // row pitch: D % 4 == 0, so rows stay 16-byte aligned
+    float* sim = smem;
+    float* rows = sim + (size_t)Js * Jt;               // [Js + Jt][P]; Js * Jt % 4 == 0 is checked by the launcher
+    float* den = rows + (size_t)(Js + Jt) * P;
+    float* corr = den + (Js + Jt);
+    float* wgt = corr + 3 * Js;
+    float* mus = wgt + Js;
+    float* mut = mus + 3 * Js;
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = kSPThreads / 32;
+    const float* xd = src_desc + (int64_t)b * Js * D;
+    const float* yd = tgt_desc + (int64_t)b * Jt * D;
+    const int R = Js + Jt, D4 = D >> 2;
+
+    for (int e = tid; e < R * D4; e += kSPThreads) {
+        const int r = e / D4, c = e - r * D4;
+        const float* row = r < Js ? xd + (int64_t)r * D : yd + (int64_t)(r - Js) * D;
+        *reinterpret_cast<float4*>(rows + (size_t)r * P + 4 * c) = __ldg(reinterpret_cast<const float4*>(row) + c);
+    }
+    for (int i = tid; i < 3 * Js; i += kSPThreads) mus[i] = src_mu[(int64_t)b * Js * 3 + i];
+    for (int i = tid; i < 3 * Jt; i += kSPThreads) mut[i] = tgt_mu[(int64_t)b * Jt * 3 + i];
+    __syncthreads();
+    // row norms (F.normalize: x / max(|x|_2, 1e-12)), lane-strided partial sums like the chunked kernel
+    for (int r = warp; r < R; r += NW) {
+        const float* row = rows + (size_t)r * P;
+        float acc = 0.f;
+        for (int d = lane; d < D; d += 32) { const float v = row[d]; acc += v * v; }
+        acc = warp_sum(acc);
+        if (lane == 0) den[r] = fmaxf(sqrtf(acc), 1e-12f);
     }
     __syncthreads();
-    for (int e = tid; e < 3 * Js; e += kSPThreads) corr_out[(int64_t)b * 3 * Js + e] = corr[e];
-
-    // 5. weighted Procrustes over the Js components (warp 0)
-    if (warp == 0) {
-        float sw = 0.f, ss[3] = {0.f, 0.f, 0.f}, sc[3] = {0.f, 0.f, 0.f};
-        for (int i = lane; i < Js; i += 32) {
-            float wi = wgt[i];
-            sw += wi;
-#pragma unroll
-            for (int a = 0; a < 3; ++a) { ss[a] += mus[3 * i + a] * wi; sc[a] += corr[a * Js + i] * wi; }
-        }
-        sw = warp_sum(sw);
-        float cs[3], ct[3];
-#pragma unroll
-        for (int a = 0; a < 3; ++a) { cs[a] = warp_sum(ss[a]) / sw; ct[a] = warp_sum(sc[a]) / sw; }
-        float cov[9];
-#pragma unroll
-        for (int i = 0; i < 9; ++i) cov[i] = 0.f;
-        for (int i = lane; i < Js; i += 32) {
-            float wi = wgt[i];
-            float sa[3], cb[3];
-#pragma unroll
-            for (int a = 0; a < 3; ++a) { sa[a] = (mus[3 * i + a] - cs[a]) * wi; cb[a] = corr[a * Js + i] - ct[a]; }
-#pragma unroll
-            for (int a = 0; a < 3; ++a)
-#pragma unroll
-                for (int c = 0; c < 3; ++c) cov[3 * a + c] += sa[a] * cb[c];
-        }
-#pragma unroll
-        for (int i = 0; i < 9; ++i) cov[i] = warp_sum(cov[i]);
-        if (lane == 0) finish_procrustes(cov, cs, ct, rot_out + (int64_t)b * 9, trans_out + (int64_t)b * 3);
+    for (int e = tid; e < R * D4; e += kSPThreads) {
+        const int r = e / D4, c = e - r * D4;
+        float4* q = reinterpret_cast<float4*>(rows + (size_t)r * P + 4 * c);
+        float4 v = *q;
+        const float dn = den[r];
+        v.x = v.x / dn; v.y = v.y / dn; v.z = v.z / dn; v.w = v.w / dn;
+        *q = v;
     }
+    __syncthreads();
+    const int npairs = Js * Jt;
+    for (int p = tid; p < npairs; p += kSPThreads) {
+        const int i = p / Jt, j = p - i * Jt;
+        const float4* xa = reinterpret_cast<const float4*>(rows + (size_t)i * P);
+        const float4* ya = reinterpret_cast<const float4*>(rows + (size_t)(Js + j) * P);
+        float a = 0.f;
+        for (int d = 0; d < D4; ++d) {
+            const float4 u = xa[d], v = ya[d];
+            a = fmaf(u.x, v.x, a); a = fmaf(u.y, v.y, a); a = fmaf(u.z, v.z, a); a = fmaf(u.w, v.w, a);
+        }
+        sim[p] = a;
+    }
+    __syncthreads();
+    if (sim_out != nullptr)
+        for (int p = tid; p < npairs; p += kSPThreads) sim_out[(int64_t)b * npairs + p] = sim[p];
+    if (head == 0) return;      // cos_similarity only
+    __syncthreads();
+    soft_head_tail(sim, corr, wgt, mus, mut, Js, Jt, temperature, b, rot_out, trans_out, corr_out);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -323,6 +409,19 @@ extern "C" __attribute__((visibility("default"))) int ogmm_rigid_transform(const
 static int launch_soft(const float* src_mu, const float* tgt_mu, const float* src_desc, const float* tgt_desc,
                        int64_t B, int64_t Js, int64_t Jt, int64_t D, float temperature, float* rot_out,
                        float* trans_out, float* corr_out, float* sim_out, int head, ogmm_stream_t stream) {
+    // both descriptor sets resident in shared memory when they fit three CTAs per SM; the chunked kernel otherwise
+    const size_t full = soft_procrustes_full_smem((int)Js, (int)Jt, (int)D);
+    const bool aligned = ((reinterpret_cast<uintptr_t>(src_desc) | reinterpret_cast<uintptr_t>(tgt_desc)) & 15) == 0;
+    if ((D & 3) == 0 && ((Js * Jt) & 3) == 0 && aligned && full <= 72 * 1024) {
+        int st = cuda_status(cudaFuncSetAttribute(soft_procrustes_full_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  (int)full), "cudaFuncSetAttribute(soft_procrustes_full_kernel)");
+        if (st != OGMM_OK) return st;
+        soft_procrustes_full_kernel<<<(unsigned)B, kSPThreads, full, as_stream(stream)>>>(
+            src_mu, tgt_mu, src_desc, tgt_desc, (int)Js, (int)Jt, (int)D, temperature, rot_out, trans_out, corr_out,
+            sim_out, head);
+        OGMM_LAUNCH_CHECK("soft_procrustes_full_kernel");
+        return OGMM_OK;
+    }
     size_t smem = soft_procrustes_smem((int)Js, (int)Jt);
     OGMM_REQUIRE(smem <= 200 * 1024, OGMM_EUNSUPPORTED,
                  "soft_procrustes: Js=%lld Jt=%lld needs %zu B of shared memory (> 200 KiB)", (long long)Js,
