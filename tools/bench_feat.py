@@ -25,5 +25,5 @@ torch.cuda.synchronize()
 ts = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(reps))
 ms = ts[len(ts) // 2]
 byts = 4.0 * B * (N * 16 + N * D + 16 * D)
-print(json.dumps({"B": B, "N": N, "D": D, "dbg": os.environ.get("OGMM_TMA_DEBUG", ""), "ms": round(ms, 4),
+print(json.dumps({"B": B, "N": N, "D": D, "no_tma": os.environ.get("OGMM_FEAT_NO_TMA", ""), "ms": round(ms, 4),
                   "GBs": round(byts / ms / 1e6, 1)}))
