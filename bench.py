@@ -169,7 +169,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    pairs = args.cpu_pairs or min(128, max(4, int(120 * 35 / (args.steps + args.warmup))))
+    pairs = args.cpu_pairs or min(256, max(4, int(120 * 90 / (args.steps + args.warmup))))
     times, cores = time_cpu(pairs, args.steps, args.warmup)
     total = sum(times)
     value = pairs * len(times) / total
@@ -381,7 +381,7 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and not args.no_cpu:
-        args.cpu_pairs = args.cpu_pairs or 128
+        args.cpu_pairs = args.cpu_pairs or 256           # the workload's own batch: ~3 s per pass on 16 cores
         times, cores = time_cpu(args.cpu_pairs, 3, 1)
         best = min(times)
         cpu = {"value": args.cpu_pairs / best, "unit": "pairs/s", "cores": cores, "kind": "port",
@@ -417,8 +417,8 @@ def main():
     ap.add_argument("--pairs", type=int, default=256, help="pairs per GPU per step")
     ap.add_argument("--distinct", type=int, default=32, help="distinct synthetic pairs generated per rank (tiled to --pairs)")
     ap.add_argument("--cpu-pairs", type=int, default=None,
-                    help="pairs per CPU step (default: 128 for the cpu_baseline leg = ~15 s of CPU work; for --impl "
-                         "reference as many as keep steps + warmup within ~2 minutes at ~35 pairs/s)")
+                    help="pairs per CPU step (default: 256 for the cpu_baseline leg = ~12 s of CPU work; for --impl "
+                         "reference as many, up to 256, as keep steps + warmup within ~2 minutes at ~90 pairs/s)")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
