@@ -62,6 +62,14 @@ int ogmm_knn_graph(const float* src, int64_t s_sb, int64_t s_sn, int64_t s_sc,
                    int64_t B, int64_t N, int64_t M, int64_t C, int64_t k, int normalize,
                    int64_t* idx_out, float* dist_out, float* edge_out, ogmm_stream_t stream);
 
+/* square_distance alone (lib/utils.py:12-34): the dense matrix dist_out (B,N,M) contiguous, same arithmetic as the
+ * selection kernels (dist_out of ogmm_knn_graph is a gather of it).  For callers outside the hot path (losses,
+ * metrics); the hot path never materialises it. */
+int ogmm_square_distance(const float* src, int64_t s_sb, int64_t s_sn, int64_t s_sc,
+                         const float* dst, int64_t d_sb, int64_t d_sn, int64_t d_sc,
+                         int64_t B, int64_t N, int64_t M, int64_t C, int normalize,
+                         float* dist_out, ogmm_stream_t stream);
+
 /* ---- K1w: feature-space kNN on the tensor cores ------------------------------------------------------
  * Same contract as ogmm_knn_graph for 32 <= C <= 256, k <= 32 (ogmm_knn_graph routes such calls here).  The Gram
  * tiles run as tcgen05 TF32 MMAs with TMEM accumulators; a guaranteed superset of the true neighbours is then
@@ -93,14 +101,12 @@ int ogmm_fps(const float* xyz, int64_t sb, int64_t sn, int64_t sc, int64_t B, in
  * :288).  The final feature M-step (:289) is ogmm_gmm_moments_feat.
  *   xyz (B,N,3) strided view; o_scores (B,N) contiguous.
  *   gamma_out (B,N,J), pi_out (B,J), mu_out (B,J,3) contiguous.
- *   The batch-coupled early exit (:99-102) is reproduced exactly: each launch records every
- *   cloud's per-iteration change, the last CTA to finish evaluates the batch means, and one
- *   persistent follow-up launch (queued on the same stream, immediate exit when not needed) re-runs
- *   from the first outer iteration whose inner count changed until the schedule stands.  No host
- *   synchronisation, no cooperative launch.  The follow-up synchronises its blocks through a
- *   barrier in the workspace and is sized so that two of them (the source and the target call of a
- *   pair, on two streams) can always be resident together; do not keep more than two clustering
- *   calls in flight on one device at the same time.
+ *   The batch-coupled early exit (:99-102) is reproduced exactly: the main launch records every
+ *   cloud's per-iteration change, its last CTA evaluates the batch means, and `iters` ordinary redo
+ *   launches queued behind it on the same stream (each an empty launch when nothing has to change, the
+ *   common case) re-run from the first outer iteration whose inner count changed until the schedule
+ *   stands.  No host synchronisation, no cooperative launch, no grid barrier: no launch waits on another
+ *   CTA, so any number of clustering calls may be in flight on one device at the same time.
  *   workspace: device scratch of at least ogmm_sinkhorn_cluster_workspace(...) bytes; contents
  *   need not be initialised.  iters_run_out (optional) (iters) int32: inner iterations per outer. */
 int64_t ogmm_sinkhorn_cluster_workspace(int64_t B, int64_t N, int64_t J, int64_t iters, int64_t max_iter);
@@ -166,7 +172,10 @@ int ogmm_soft_procrustes(const float* src_mu, const float* tgt_mu, const float* 
                          float* rot_out, float* trans_out, float* corr_out, float* sim_out,
                          ogmm_stream_t stream);
 
-/* Cosine similarity alone (lib/utils.py:222-226): x (B,N,D), y (B,M,D) contiguous -> (B,N,M). */
+/* Cosine similarity alone (lib/utils.py:222-226): x (B,N,D), y (B,M,D) contiguous -> (B,N,M).
+ * Sized for component descriptors (the GMMSVD head, N = Js, M = Jt): one CTA holds the N x M similarity tile in
+ * shared memory, so N * M is limited to about 45,000 entries (e.g. 200 x 200); larger calls return
+ * OGMM_EUNSUPPORTED.  (The model's dense N x M point similarity, models/gmmreg.py:75, stays a PyTorch einsum.) */
 int ogmm_cos_similarity(const float* x, const float* y, int64_t B, int64_t N, int64_t M, int64_t D,
                         float* sim_out, ogmm_stream_t stream);
 

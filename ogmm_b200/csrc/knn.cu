@@ -147,7 +147,7 @@ knn3_kernel(const float* __restrict__ src, int64_t s_sb, int64_t s_sn, int64_t s
 #pragma unroll
     for (int j = 0; j < K; ++j) {
         if (j < k) {
-            io[j] = top.i[j];
+            io[j] = top.i[j];                                          // unfilled slots (NaN distances) hold index 0
             if (dout) dout[j] = top.d[j];
             if (eo) {
                 const float* p = sb + (int64_t)top.i[j] * s_sn;       // self graph: neighbours live in src
@@ -339,6 +339,87 @@ edge_gather_kernel(const float* __restrict__ x, int64_t sb, int64_t sc, int64_t 
     out[(int64_t)b * per_cloud + e] = v;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// square_distance alone (lib/utils.py:12-34): the dense (B,N,M) matrix for callers that want it (losses, metrics).
+// Same arithmetic as the selection kernels -- ((-2 s.d) + |s|^2) + |d|^2, FMA chain over c, clamp 1e-12; or
+// 2 + (-2 s.d) with normalize -- so dist_out of ogmm_knn_graph is a gather of this matrix, bit for bit.
+// CTA = 32 queries x 128 candidates; a thread owns 4 consecutive candidates of 4 queries; candidate coordinates are
+// staged (already scaled by -2) in shared memory, stores are 16-byte and coalesced along M.  Write-bound.
+constexpr int kSqQ = 32, kSqC = 128, kSqChunk = 32;
+
+__global__ void __launch_bounds__(256)
+square_distance_kernel(const float* __restrict__ src, int64_t s_sb, int64_t s_sn, int64_t s_sc,
+                       const float* __restrict__ dst, int64_t d_sb, int64_t d_sn, int64_t d_sc,
+                       int N, int M, int C, int normalize, float* __restrict__ out) {
+    __shared__ float s_q[kSqChunk][kSqQ + 1];
+    __shared__ float s_c[kSqChunk][kSqC + 4];
+    __shared__ float s_qn[kSqQ], s_cn[kSqC];
+    const int b = blockIdx.z, q0 = blockIdx.y * kSqQ, m0 = blockIdx.x * kSqC, tid = threadIdx.x;
+    const float* sb = src + (int64_t)b * s_sb;
+    const float* db = dst + (int64_t)b * d_sb;
+    const int tq = (tid >> 5) * 4, tc = (tid & 31) * 4;
+    if (tid < kSqQ) {
+        float acc = 0.f;
+        if (q0 + tid < N)
+            for (int c = 0; c < C; ++c) { const float v = sb[(int64_t)(q0 + tid) * s_sn + (int64_t)c * s_sc]; acc = __fadd_rn(acc, __fmul_rn(v, v)); }
+        s_qn[tid] = acc;
+    } else if (tid < kSqQ + kSqC) {
+        const int m = tid - kSqQ;
+        float acc = 0.f;
+        if (m0 + m < M)
+            for (int c = 0; c < C; ++c) { const float v = db[(int64_t)(m0 + m) * d_sn + (int64_t)c * d_sc]; acc = __fadd_rn(acc, __fmul_rn(v, v)); }
+        s_cn[m] = acc;
+    }
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int c0 = 0; c0 < C; c0 += kSqChunk) {
+        __syncthreads();
+        for (int e = tid; e < kSqQ * kSqChunk; e += 256) {
+            const int c = e / kSqQ, r = e - c * kSqQ;
+            s_q[c][r] = (q0 + r < N && c0 + c < C) ? sb[(int64_t)(q0 + r) * s_sn + (int64_t)(c0 + c) * s_sc] : 0.f;
+        }
+        for (int e = tid; e < kSqC * kSqChunk; e += 256) {
+            const int c = e / kSqC, r = e - c * kSqC;
+            s_c[c][r] = (m0 + r < M && c0 + c < C) ? -2.f * db[(int64_t)(m0 + r) * d_sn + (int64_t)(c0 + c) * d_sc] : 0.f;
+        }
+        __syncthreads();
+        const int cw = min(kSqChunk, C - c0);
+        for (int c = 0; c < cw; ++c) {
+            const float4 cv = *reinterpret_cast<const float4*>(&s_c[c][tc]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float qv = s_q[c][tq + i];
+                if (c0 + c == 0) {          // the first product is rounded on its own (a GEMM's accumulator starts at 0)
+                    acc[i][0] = __fmul_rn(qv, cv.x); acc[i][1] = __fmul_rn(qv, cv.y);
+                    acc[i][2] = __fmul_rn(qv, cv.z); acc[i][3] = __fmul_rn(qv, cv.w);
+                } else {
+                    acc[i][0] = fmaf(qv, cv.x, acc[i][0]); acc[i][1] = fmaf(qv, cv.y, acc[i][1]);
+                    acc[i][2] = fmaf(qv, cv.z, acc[i][2]); acc[i][3] = fmaf(qv, cv.w, acc[i][3]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int q = q0 + tq + i;
+        if (q >= N) continue;
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (normalize) v[j] = __fadd_rn(acc[i][j], 2.0f);
+            else v[j] = fmaxf(__fadd_rn(__fadd_rn(acc[i][j], s_qn[tq + i]), s_cn[tc + j]), 1e-12f);
+        }
+        float* o = out + ((int64_t)b * N + q) * M + m0 + tc;
+        if ((M & 3) == 0 && m0 + tc + 3 < M) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+        else
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (m0 + tc + j < M) o[j] = v[j];
+    }
+}
+
 }  // namespace ogmm
 
 using namespace ogmm;
@@ -364,7 +445,8 @@ extern "C" __attribute__((visibility("default"))) int ogmm_knn_graph(const float
     OGMM_REQUIRE(k <= 64, OGMM_EUNSUPPORTED, "ogmm_knn_graph: k=%lld > 64", (long long)k);
     if (B == 0) return OGMM_OK;
     OGMM_REQUIRE(src && dst && idx_out, OGMM_EINVAL, "ogmm_knn_graph: null pointer");
-    OGMM_REQUIRE(edge_out == nullptr || (N == M), OGMM_EINVAL, "ogmm_knn_graph: edge_out needs a self graph (N == M)");
+    OGMM_REQUIRE(edge_out == nullptr || (N == M && src == dst && s_sb == d_sb && s_sn == d_sn && s_sc == d_sc), OGMM_EINVAL,
+                 "ogmm_knn_graph: edge_out needs a self graph (dst must be the same view as src)");
     cudaStream_t s = as_stream(stream);
     // 3-D clouds of up to 4096 points: sorted sweep with slab pruning (knn_sweep.cu); OGMM_KNN_EXHAUSTIVE=1
     // forces the exhaustive kernel (same results; kept for larger clouds and for A/B timing)
@@ -450,4 +532,20 @@ extern "C" __attribute__((visibility("default"))) int ogmm_knn_wide(const float*
     OGMM_REQUIRE(src && dst && idx_out, OGMM_EINVAL, "ogmm_knn_wide: null pointer");
     return ogmm_launch_knn_wide(src, s_sb, s_sn, s_sc, dst, d_sb, d_sn, d_sc, B, N, M, C, k, normalize, idx_out, dist_out,
                                 fallback_count, as_stream(stream));
+}
+
+extern "C" __attribute__((visibility("default"))) int ogmm_square_distance(const float* src, int64_t s_sb, int64_t s_sn, int64_t s_sc,
+                                                                         const float* dst, int64_t d_sb, int64_t d_sn, int64_t d_sc,
+                                                                         int64_t B, int64_t N, int64_t M, int64_t C, int normalize,
+                                                                         float* dist_out, ogmm_stream_t stream) {
+    OGMM_REQUIRE(B >= 0 && N >= 1 && M >= 1 && C >= 1 && N < (1ll << 31) && M < (1ll << 31) && B < 65536, OGMM_EINVAL,
+                 "ogmm_square_distance: bad sizes B=%lld N=%lld M=%lld C=%lld", (long long)B, (long long)N, (long long)M, (long long)C);
+    if (B == 0) return OGMM_OK;
+    OGMM_REQUIRE(src && dst && dist_out, OGMM_EINVAL, "ogmm_square_distance: null pointer");
+    OGMM_REQUIRE((N + kSqQ - 1) / kSqQ < 65536, OGMM_EUNSUPPORTED, "ogmm_square_distance: N=%lld too large", (long long)N);
+    dim3 grid((unsigned)((M + kSqC - 1) / kSqC), (unsigned)((N + kSqQ - 1) / kSqQ), (unsigned)B);
+    square_distance_kernel<<<grid, 256, 0, as_stream(stream)>>>(src, s_sb, s_sn, s_sc, dst, d_sb, d_sn, d_sc, (int)N, (int)M,
+                                                                 (int)C, normalize, dist_out);
+    OGMM_LAUNCH_CHECK("square_distance_kernel");
+    return OGMM_OK;
 }

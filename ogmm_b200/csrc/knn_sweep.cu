@@ -348,7 +348,7 @@ knn3_sweep_kernel(const float* __restrict__ src, int64_t s_sb, int64_t s_sn, int
 #pragma unroll
             for (int j = 0; j < K; ++j) {
                 if (j < k) {
-                    const int nb = (int)(unsigned)(top.key[j] & 0xffffffffull);
+                    const int nb = (int)min((unsigned)(top.key[j] & 0xffffffffull), (unsigned)(M - 1));   // an unfilled slot (NaN keys) stays in range
                     io[j] = nb;
                     if (dout) dout[j] = __uint_as_float((unsigned)(top.key[j] >> 32));
                     if (eo) {

@@ -7,32 +7,43 @@
 //
 // These are latency-bound (tens of KB per pair); the point is to remove the reference's
 // device->host->device SVD round trip and its ~20 tiny launches, not to chase a roofline.
-// Sums are accumulated in fp32 like the reference; the 3x3 SVD and the final 3x3 algebra run in
-// fp64 registers (negligible cost, keeps the rotation well inside the 1e-3 deg budget).
+// Everything after the fp32 inputs -- weighted centroids, the 3x3 cross-covariance, the SVD and t = c_t - R c_s --
+// runs in fp64 registers (a few hundred flops per pair): the result is the correctly rounded answer for the fp32
+// inputs, so its distance to the fp32 reference is the REFERENCE's own rounding error (tests print that spread:
+// the fp32-vs-fp64 difference of the reference's op sequence) and rotation / translation stay inside the
+// 1e-3 deg / 1e-5 x scale budget against the fp64 arbiter.
 #include "common.cuh"
 #include "svd3.cuh"
 
 namespace ogmm {
 
-// Shared tail: fp32 covariance (row-major 9) + centroids -> R, t.  Called by one lane.
-__device__ __forceinline__ void finish_procrustes(const float* cov_in, const float* cs, const float* ct,
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+
+// Shared tail: covariance (row-major 9) + centroids -> R, t.  Called by one lane.  The reference adds 1e-5 * eye to an
+// fp32 covariance (lib/se3.py:275): the diagonal is rounded to fp32 before the add so that term enters identically.
+__device__ __forceinline__ void finish_procrustes(const double* cov_in, const double* cs, const double* ct,
                                                   float* rot_out, float* trans_out) {
     double cov[9];
 #pragma unroll
     for (int i = 0; i < 9; ++i) {
-        float c = nan_to_num(cov_in[i], 0.f);
-        if (i % 4 == 0) c = c + 1e-5f;                       // + 1e-5 * eye, in fp32 like the reference
-        cov[i] = (double)c;
+        double c = cov_in[i];
+        if (c != c) c = 0.0;                                     // nan_to_num(cov)
+        else if (c > 3.402823466e+38) c = 3.402823466e+38;
+        else if (c < -3.402823466e+38) c = -3.402823466e+38;
+        if (i % 4 == 0) c = c + 1e-5;
+        cov[i] = c;
     }
     double R[9];
     rotation_from_cov_ogmm(cov, R);
 #pragma unroll
     for (int i = 0; i < 9; ++i) rot_out[i] = (float)R[i];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        float r0 = (float)R[3 * i], r1 = (float)R[3 * i + 1], r2 = (float)R[3 * i + 2];
-        trans_out[i] = -(r0 * cs[0] + r1 * cs[1] + r2 * cs[2]) + ct[i];
-    }
+    for (int i = 0; i < 3; ++i)
+        trans_out[i] = (float)(-(R[3 * i] * cs[0] + R[3 * i + 1] * cs[1] + R[3 * i + 2] * cs[2]) + ct[i]);
 }
 
 __global__ void __launch_bounds__(128)
@@ -47,33 +58,33 @@ rigid_transform_kernel(const float* __restrict__ src, int64_t s_sb, int64_t s_sc
     const float* c = corr + (int64_t)warp * c_sb;
     const float* w = weight + (int64_t)warp * w_sb;
 
-    float sw = 0.f, ss[3] = {0.f, 0.f, 0.f}, sc[3] = {0.f, 0.f, 0.f};
+    double sw = 0.0, ss[3] = {0.0, 0.0, 0.0}, sc[3] = {0.0, 0.0, 0.0};
     for (int i = lane; i < n; i += 32) {
-        float wi = w[i * w_sn];
+        const double wi = (double)w[i * w_sn];
         sw += wi;
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-            ss[a] += s[a * s_sc + i * s_sn] * wi;
-            sc[a] += c[a * c_sc + i * c_sn] * wi;
+            ss[a] += (double)s[a * s_sc + i * s_sn] * wi;
+            sc[a] += (double)c[a * c_sc + i * c_sn] * wi;
         }
     }
-    sw = warp_sum(sw);
-    float cs[3], ct[3];
+    sw = warp_sum_d(sw);
+    double cs[3], ct[3];
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-        cs[a] = warp_sum(ss[a]) / sw;
-        ct[a] = warp_sum(sc[a]) / sw;
+        cs[a] = warp_sum_d(ss[a]) / sw;
+        ct[a] = warp_sum_d(sc[a]) / sw;
     }
-    float cov[9];
+    double cov[9];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) cov[i] = 0.f;
+    for (int i = 0; i < 9; ++i) cov[i] = 0.0;
     for (int i = lane; i < n; i += 32) {
-        float wi = w[i * w_sn];
-        float sa[3], cb[3];
+        const double wi = (double)w[i * w_sn];
+        double sa[3], cb[3];
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-            sa[a] = (s[a * s_sc + i * s_sn] - cs[a]) * wi;
-            cb[a] = c[a * c_sc + i * c_sn] - ct[a];
+            sa[a] = ((double)s[a * s_sc + i * s_sn] - cs[a]) * wi;
+            cb[a] = (double)c[a * c_sc + i * c_sn] - ct[a];
         }
 #pragma unroll
         for (int a = 0; a < 3; ++a)
@@ -81,7 +92,7 @@ rigid_transform_kernel(const float* __restrict__ src, int64_t s_sb, int64_t s_sc
             for (int b = 0; b < 3; ++b) cov[3 * a + b] += sa[a] * cb[b];
     }
 #pragma unroll
-    for (int i = 0; i < 9; ++i) cov[i] = warp_sum(cov[i]);
+    for (int i = 0; i < 9; ++i) cov[i] = warp_sum_d(cov[i]);
     if (lane == 0) finish_procrustes(cov, cs, ct, rot_out + (int64_t)warp * 9, trans_out + (int64_t)warp * 3);
 }
 
@@ -131,32 +142,32 @@ __device__ __forceinline__ void soft_head_tail(float* sim, float* corr, float* w
 
     // 5. weighted Procrustes over the Js components (warp 0)
     if (warp == 0) {
-        float sw = 0.f, ss[3] = {0.f, 0.f, 0.f}, sc[3] = {0.f, 0.f, 0.f};
+        double sw = 0.0, ss[3] = {0.0, 0.0, 0.0}, sc[3] = {0.0, 0.0, 0.0};
         for (int i = lane; i < Js; i += 32) {
-            float wi = wgt[i];
+            const double wi = (double)wgt[i];
             sw += wi;
 #pragma unroll
-            for (int a = 0; a < 3; ++a) { ss[a] += mus[3 * i + a] * wi; sc[a] += corr[a * Js + i] * wi; }
+            for (int a = 0; a < 3; ++a) { ss[a] += (double)mus[3 * i + a] * wi; sc[a] += (double)corr[a * Js + i] * wi; }
         }
-        sw = warp_sum(sw);
-        float cs[3], ct[3];
+        sw = warp_sum_d(sw);
+        double cs[3], ct[3];
 #pragma unroll
-        for (int a = 0; a < 3; ++a) { cs[a] = warp_sum(ss[a]) / sw; ct[a] = warp_sum(sc[a]) / sw; }
-        float cov[9];
+        for (int a = 0; a < 3; ++a) { cs[a] = warp_sum_d(ss[a]) / sw; ct[a] = warp_sum_d(sc[a]) / sw; }
+        double cov[9];
 #pragma unroll
-        for (int i = 0; i < 9; ++i) cov[i] = 0.f;
+        for (int i = 0; i < 9; ++i) cov[i] = 0.0;
         for (int i = lane; i < Js; i += 32) {
-            float wi = wgt[i];
-            float sa[3], cb[3];
+            const double wi = (double)wgt[i];
+            double sa[3], cb[3];
 #pragma unroll
-            for (int a = 0; a < 3; ++a) { sa[a] = (mus[3 * i + a] - cs[a]) * wi; cb[a] = corr[a * Js + i] - ct[a]; }
+            for (int a = 0; a < 3; ++a) { sa[a] = ((double)mus[3 * i + a] - cs[a]) * wi; cb[a] = (double)corr[a * Js + i] - ct[a]; }
 #pragma unroll
             for (int a = 0; a < 3; ++a)
 #pragma unroll
                 for (int c = 0; c < 3; ++c) cov[3 * a + c] += sa[a] * cb[c];
         }
 #pragma unroll
-        for (int i = 0; i < 9; ++i) cov[i] = warp_sum(cov[i]);
+        for (int i = 0; i < 9; ++i) cov[i] = warp_sum_d(cov[i]);
         if (lane == 0) finish_procrustes(cov, cs, ct, rot_out + (int64_t)b * 9, trans_out + (int64_t)b * 3);
     }
 }
@@ -191,8 +202,10 @@ soft_procrustes_kernel(const float* __restrict__ src_mu, const float* __restrict
         acc = warp_sum(acc);
         if (lane == 0) den[r] = fmaxf(sqrtf(acc), 1e-12f);
     }
-    for (int i = tid; i < 3 * Js; i += kSPThreads) mus[i] = src_mu[(int64_t)b * Js * 3 + i];
-    for (int i = tid; i < 3 * Jt; i += kSPThreads) mut[i] = tgt_mu[(int64_t)b * Jt * 3 + i];
+    if (head != 0) {                                   // cosine-only calls pass no centroids
+        for (int i = tid; i < 3 * Js; i += kSPThreads) mus[i] = src_mu[(int64_t)b * Js * 3 + i];
+        for (int i = tid; i < 3 * Jt; i += kSPThreads) mut[i] = tgt_mu[(int64_t)b * Jt * 3 + i];
+    }
     __syncthreads();
 
     // 2. similarity, pair-block by pair-block, descriptor chunk by chunk
@@ -281,8 +294,10 @@ soft_procrustes_full_kernel(const float* __restrict__ src_mu, const float* __res
         const float* row = r < Js ? xd + (int64_t)r * D : yd + (int64_t)(r - Js) * D;
         *reinterpret_cast<float4*>(rows + (size_t)r * P + 4 * c) = __ldg(reinterpret_cast<const float4*>(row) + c);
     }
-    for (int i = tid; i < 3 * Js; i += kSPThreads) mus[i] = src_mu[(int64_t)b * Js * 3 + i];
-    for (int i = tid; i < 3 * Jt; i += kSPThreads) mut[i] = tgt_mu[(int64_t)b * Jt * 3 + i];
+    if (head != 0) {                                   // cosine-only calls pass no centroids
+        for (int i = tid; i < 3 * Js; i += kSPThreads) mus[i] = src_mu[(int64_t)b * Js * 3 + i];
+        for (int i = tid; i < 3 * Jt; i += kSPThreads) mut[i] = tgt_mu[(int64_t)b * Jt * 3 + i];
+    }
     __syncthreads();
     // row norms (F.normalize: x / max(|x|_2, 1e-12)), lane-strided partial sums like the chunked kernel
     for (int r = warp; r < R; r += NW) {
@@ -323,10 +338,10 @@ soft_procrustes_full_kernel(const float* __restrict__ src_mu, const float* __res
 }
 
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void inverse3(const float* m, float* inv) {
-    float c00 = m[4] * m[8] - m[5] * m[7], c01 = m[5] * m[6] - m[3] * m[8], c02 = m[3] * m[7] - m[4] * m[6];
-    float det = m[0] * c00 + m[1] * c01 + m[2] * c02;
-    float r = 1.0f / det;
+__device__ __forceinline__ void inverse3(const double* m, double* inv) {
+    const double c00 = m[4] * m[8] - m[5] * m[7], c01 = m[5] * m[6] - m[3] * m[8], c02 = m[3] * m[7] - m[4] * m[6];
+    const double det = m[0] * c00 + m[1] * c01 + m[2] * c02;
+    const double r = 1.0 / det;
     inv[0] = c00 * r; inv[1] = (m[2] * m[7] - m[1] * m[8]) * r; inv[2] = (m[1] * m[5] - m[2] * m[4]) * r;
     inv[3] = c01 * r; inv[4] = (m[0] * m[8] - m[2] * m[6]) * r; inv[5] = (m[2] * m[3] - m[0] * m[5]) * r;
     inv[6] = c02 * r; inv[7] = (m[1] * m[6] - m[0] * m[7]) * r; inv[8] = (m[0] * m[4] - m[1] * m[3]) * r;
@@ -342,25 +357,27 @@ gmm_register_kernel(const float* __restrict__ pi_s, const float* __restrict__ mu
     const float* ms = mu_s + (int64_t)warp * J * 3;
     const float* mt = mu_t + (int64_t)warp * J * 3;
     const float* sg = sigma_t + (int64_t)warp * J * 9;
-    float cs[3] = {0.f, 0.f, 0.f}, ct[3] = {0.f, 0.f, 0.f};
+    double cs[3] = {0.0, 0.0, 0.0}, ct[3] = {0.0, 0.0, 0.0};
     for (int j = lane; j < J; j += 32) {
-        float p = pi[j];
+        const double p = (double)pi[j];
 #pragma unroll
-        for (int a = 0; a < 3; ++a) { cs[a] = fmaf(p, ms[3 * j + a], cs[a]); ct[a] = fmaf(p, mt[3 * j + a], ct[a]); }
+        for (int a = 0; a < 3; ++a) { cs[a] += p * (double)ms[3 * j + a]; ct[a] += p * (double)mt[3 * j + a]; }
     }
 #pragma unroll
-    for (int a = 0; a < 3; ++a) { cs[a] = warp_sum(cs[a]); ct[a] = warp_sum(ct[a]); }
-    float M[9];
+    for (int a = 0; a < 3; ++a) { cs[a] = warp_sum_d(cs[a]); ct[a] = warp_sum_d(ct[a]); }
+    double M[9];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) M[i] = 0.f;
+    for (int i = 0; i < 9; ++i) M[i] = 0.0;
     for (int j = lane; j < J; j += 32) {
-        float p = pi[j];
-        float a[3], bt[3], inv[9];
+        const double p = (double)pi[j];
+        double a[3], bt[3], sgd[9], inv[9];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) { a[c] = p * (ms[3 * j + c] - cs[c]); bt[c] = mt[3 * j + c] - ct[c]; }
-        inverse3(sg + 9 * j, inv);
+        for (int c = 0; c < 3; ++c) { a[c] = p * ((double)ms[3 * j + c] - cs[c]); bt[c] = (double)mt[3 * j + c] - ct[c]; }
+#pragma unroll
+        for (int c = 0; c < 9; ++c) sgd[c] = (double)sg[9 * j + c];
+        inverse3(sgd, inv);
         // (a b^T) Sigma^-1 = a (b^T Sigma^-1)
-        float row[3];
+        double row[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) row[c] = bt[0] * inv[c] + bt[1] * inv[3 + c] + bt[2] * inv[6 + c];
 #pragma unroll
@@ -369,18 +386,23 @@ gmm_register_kernel(const float* __restrict__ pi_s, const float* __restrict__ mu
             for (int c = 0; c < 3; ++c) M[3 * r + c] += a[r] * row[c];
     }
 #pragma unroll
-    for (int i = 0; i < 9; ++i) M[i] = warp_sum(M[i]);
+    for (int i = 0; i < 9; ++i) M[i] = warp_sum_d(M[i]);
     if (lane == 0) {
         double Md[9], R[9];
 #pragma unroll
-        for (int i = 0; i < 9; ++i) Md[i] = (double)(nan_to_num(M[i], 0.f) + 1e-4f);
+        for (int i = 0; i < 9; ++i) {
+            double m = M[i];
+            if (m != m) m = 0.0;                                   // nan_to_num(Ms, nan=0) + 1e-4 on all nine entries
+            else if (m > 3.402823466e+38) m = 3.402823466e+38;
+            else if (m < -3.402823466e+38) m = -3.402823466e+38;
+            Md[i] = m + 1e-4;
+        }
         rotation_from_cov_deepgmr(Md, R);
         float* T = tf_out + (int64_t)warp * 16;
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
-            float r0 = (float)R[3 * r], r1 = (float)R[3 * r + 1], r2 = (float)R[3 * r + 2];
-            T[4 * r] = r0; T[4 * r + 1] = r1; T[4 * r + 2] = r2;
-            T[4 * r + 3] = ct[r] - (r0 * cs[0] + r1 * cs[1] + r2 * cs[2]);
+            T[4 * r] = (float)R[3 * r]; T[4 * r + 1] = (float)R[3 * r + 1]; T[4 * r + 2] = (float)R[3 * r + 2];
+            T[4 * r + 3] = (float)(ct[r] - (R[3 * r] * cs[0] + R[3 * r + 1] * cs[1] + R[3 * r + 2] * cs[2]));
         }
         T[12] = 0.f; T[13] = 0.f; T[14] = 0.f; T[15] = 1.f;
     }
@@ -457,7 +479,7 @@ extern "C" __attribute__((visibility("default"))) int ogmm_cos_similarity(const 
                  "ogmm_cos_similarity: bad sizes");
     if (B == 0) return OGMM_OK;
     OGMM_REQUIRE(x && y && sim_out, OGMM_EINVAL, "ogmm_cos_similarity: null pointer");
-    return launch_soft(x, y, x, y, B, N, M, D, 1.f, nullptr, nullptr, nullptr, sim_out, 0, stream);
+    return launch_soft(nullptr, nullptr, x, y, B, N, M, D, 1.f, nullptr, nullptr, nullptr, sim_out, 0, stream);
 }
 
 extern "C" __attribute__((visibility("default"))) int ogmm_gmm_register(const float* pi_s, const float* mu_s, const float* mu_t, const float* sigma_t,

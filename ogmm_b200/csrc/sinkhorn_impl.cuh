@@ -31,11 +31,15 @@
 // through the exit test.  The main launch runs every Sinkhorn call for max_iter iterations and records
 // each cloud's change per (outer, inner) iteration; the last CTA to finish evaluates the batch means in
 // order and, at the first (outer o, inner i) with mean < thresh and i+1 below the count that was run,
-// stores n_inner[o] = i+1 and resume = o.  ONE follow-up launch is always queued: a persistent kernel
-// (ordinary launch, grid <= co-resident capacity) that returns at once when nothing has to change (the
-// common case) and otherwise re-runs from the centroids saved at the start of outer iteration `resume`,
-// re-evaluates, and repeats behind a software grid barrier until the schedule is certified.  The result is bit-identical to running the
-// exit test inline, and deterministic (fixed-order reductions, no float atomics).
+// stores n_inner[o] = i+1 and resume = o.  It is followed by `iters` ordinary REDO launches on the same stream:
+// each one returns at once when the schedule already stands (the common case: resume == iters) and
+// otherwise re-runs every cloud from the centroids saved at the start of outer iteration `resume`, after
+// which its last CTA re-evaluates the means.  A redo round certifies at least one more outer iteration (the
+// re-run of iteration `resume` repeats the first n_inner[resume] recorded iterations exactly), so `iters`
+// rounds always suffice.  No launch ever waits on another CTA: there is no grid barrier and no co-residency
+// requirement, so any number of calls may be in flight on a device (streams, MPS partitions, green contexts).
+// The result is bit-identical to running the exit test inline, and deterministic (fixed-order reductions, no
+// float atomics).
 #pragma once
 
 #include "common.cuh"
@@ -51,7 +55,7 @@ struct ClusterWsLayout {
 __host__ __device__ inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 __host__ __device__ inline ClusterWsLayout cluster_ws_layout(int64_t B, int64_t J, int64_t iters, int64_t max_iter) {
     ClusterWsLayout l;
-    l.state_off = 0;                                         // int32[16]: [0]=resume [1]=done counter [2]=rescues [3],[4]=grid barrier
+    l.state_off = 0;                                         // int32[16]: [0]=resume [1]=done counter [2]=rescues
     l.ninner_off = 64;                                       // int32[iters]
     l.means_off = align_up(l.ninner_off + 4 * iters, 256);   // float[iters][max_iter] batch means
     l.diffs_off = align_up(l.means_off + 4 * iters * max_iter, 256);   // float[iters][max_iter][B]
@@ -836,32 +840,11 @@ __device__ __forceinline__ void verify_schedule(const SinkhornParams& P, int res
     __syncthreads();
 }
 
-// Grid-wide barrier of the follow-up launch: arrive counter + generation in the workspace header.  The launch is an
-// ordinary one with grid <= the kernel's co-resident capacity, NOT a cooperative launch: a cooperative launch has to
-// wait until the whole grid fits at once, which stalls it behind whatever the other stream of a pair is running
-// (measured: step time bimodal 1.47 / 1.86 ms with it, 1.44 ms without).  Blocks that find nothing to redo return
-// before touching the barrier -- the common case -- and those that do spin are all scheduled eventually, because the
-// kernels they share the GPU with never wait on this stream.
-__device__ __forceinline__ void grid_barrier(int32_t* count, int32_t* gen, int nblocks) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        const int g = *reinterpret_cast<volatile int32_t*>(gen);
-        if (atomicAdd(count, 1) == nblocks - 1) {
-            atomicExch(count, 0);
-            __threadfence();
-            atomicAdd(gen, 1);
-        } else {
-            while (*reinterpret_cast<volatile int32_t*>(gen) == g) __nanosleep(100);
-        }
-        __threadfence();
-    }
-    __syncthreads();
-}
-
-// mode 0: main launch, one CTA per cloud, last CTA to finish evaluates the exit test.
-// mode 1: persistent follow-up (grid <= co-resident capacity); returns at once when the schedule of the main launch
-// stands.  (One kernel for both so the cloud body is instantiated once.)
+// mode 0: main launch, one CTA per cloud, every Sinkhorn call runs max_iter iterations.
+// mode 1: redo round: returns at once when the schedule stands, otherwise re-runs from outer iteration state[0]
+//         with the inner counts of n_inner[].
+// In both modes the last CTA to finish evaluates the batch-mean exit test and publishes the next `resume`.
+// (One kernel for both so the cloud body is instantiated once.)
 template <int NT, int PPT, bool kCluster, bool kFast, bool kExactJ>
 __global__ void __launch_bounds__(NT, (kFast && NT == 256) ? 2 : 1)
 sinkhorn_kernel(SinkhornParams P, int mode) {
@@ -873,27 +856,17 @@ sinkhorn_kernel(SinkhornParams P, int mode) {
     }
     const int Jp = kFast ? 16 : (P.J + kJC - 1) / kJC * kJC;
     const Smem S = carve_smem<NT>(smem_raw, Jp);
-    while (resume < P.iters) {
-        for (int b = blockIdx.x; b < P.B; b += gridDim.x) process_cloud<NT, PPT, kCluster, kFast, kExactJ>(P, S, b, resume, mode == 0);
+    for (int b = blockIdx.x; b < P.B; b += gridDim.x) process_cloud<NT, PPT, kCluster, kFast, kExactJ>(P, S, b, resume, mode == 0);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int prev = atomicAdd(&P.state[1], 1);
+        S.misc[5] = (prev == (int)gridDim.x - 1) ? 1.f : 0.f;
+    }
+    __syncthreads();
+    if (S.misc[5] != 0.f) {
         __threadfence();
-        if (mode == 0) {
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                const int prev = atomicAdd(&P.state[1], 1);
-                S.misc[5] = (prev == (int)gridDim.x - 1) ? 1.f : 0.f;
-            }
-            __syncthreads();
-            if (S.misc[5] != 0.f) {
-                __threadfence();
-                verify_schedule<NT>(P, 0, true);
-            }
-            return;
-        }
-        grid_barrier(P.state + 3, P.state + 4, (int)gridDim.x);
-        if (blockIdx.x == 0) verify_schedule<NT>(P, resume, false);
-        __threadfence();
-        grid_barrier(P.state + 3, P.state + 4, (int)gridDim.x);
-        resume = __ldcg(P.state);
+        verify_schedule<NT>(P, resume, mode == 0);       // also resets the done counter for the next round
     }
 }
 
@@ -932,23 +905,14 @@ static inline int launch_sinkhorn_variant(SinkhornParams P, cudaStream_t s) {
     kern<<<(unsigned)P.B, NT, smem, s>>>(P, 0);
     st = cuda_status(cudaGetLastError(), "sinkhorn_kernel (main launch)");
     if (st != OGMM_OK) return st;
-    // Follow-up grid: one CTA per SM.  The kernel fits at least one CTA per SM, so TWO such grids are always
-    // co-resident together -- the source and target calls of a pair may both sit in their barrier at once without
-    // starving each other (a spinning block keeps its SM slot).  More than two clustering calls of one device in
-    // flight at the same time, all of them hitting the early exit, is outside this guarantee (include/ogmm_b200.h).
-    int dev = 0, sms = 0, per_sm = 0;
-    st = cuda_status(cudaGetDevice(&dev), "cudaGetDevice");
-    if (st != OGMM_OK) return st;
-    st = cuda_status(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "cudaDeviceGetAttribute");
-    if (st != OGMM_OK) return st;
-    st = cuda_status(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem), "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
-    if (st != OGMM_OK) return st;
-    OGMM_REQUIRE(per_sm >= 1, OGMM_ECUDA, "sinkhorn fix-up kernel does not fit on an SM");
-    int grid = per_sm >= 2 ? sms : sms / 2;
-    if (grid > P.B) grid = P.B;
-    if (grid < 1) grid = 1;
-    kern<<<(unsigned)grid, NT, smem, s>>>(P, 1);
-    return cuda_status(cudaGetLastError(), "sinkhorn_kernel (follow-up launch)");
+    // Redo rounds (see the header comment): each certifies at least one more outer iteration, `iters` always suffice;
+    // a round whose schedule already stands is an empty launch (every CTA reads one word and returns).
+    for (int r = 0; r < P.iters; ++r) {
+        kern<<<(unsigned)P.B, NT, smem, s>>>(P, 1);
+        st = cuda_status(cudaGetLastError(), "sinkhorn_kernel (redo round)");
+        if (st != OGMM_OK) return st;
+    }
+    return OGMM_OK;
 }
 
 template <bool kCluster>

@@ -8,10 +8,28 @@ section 8(b)).  ``install()`` rebinds the hot-path names in each of those namesp
     import lib.utils, lib.se3, models.dgcnn, models.attn, models.gmmreg, lib.loss, baseline.deepgmr
     import ogmm_b200.install as inst
     inst.install()            # after the reference modules are imported
+    inst.install(model=net)   # ... and re-class the GMMSVD / Clustering instances of an existing model
+
+Two things to know:
+
+* **Training keeps working.**  The kernels are forward / inference code.  A patched name is a dispatcher: when
+  autograd is recording and an argument requires grad (``train.py:57-75``: the loss calls ``gmm_params``,
+  ``get_local_corrs``; the model differentiates through ``gmm_params(gamma, feats)``, ``GMMSVD`` and
+  ``compute_rigid_transformation``) the call goes to the reference's own function that the name held before -- exactly
+  what would have run without ``install()``.  Replacements that carry their own backward (``gmm_params`` on wide
+  features, see ``ogmm_b200/autograd.py``) take those calls themselves.  Under ``torch.no_grad()`` / inference every
+  call runs on the kernels.
+* **Classes.**  ``models.gmmreg.Clustering`` and ``GMMSVD`` are replaced by subclasses of ``ogmm_b200.modules`` that
+  dispatch the same way; they take effect for models constructed AFTER ``install()``.  A model built earlier still
+  benefits (its modules call the patched function names), and ``install(model=net)`` additionally switches the class
+  of its existing ``GMMSVD`` / ``Clustering`` instances so the fused registration-head kernel is used.
 """
 from __future__ import annotations
 
+import functools
 import sys
+
+import torch
 
 from . import modules as _modules
 from . import se3 as _se3
@@ -34,10 +52,52 @@ PATCH_TABLE = {
 }
 
 _saved = {}
+_reclassed = []
 
 
-def install(modules=None):
-    """Rebind the hot-path names in every already-imported reference module.  Returns the list patched."""
+def _needs_grad(args, kwargs):
+    if not torch.is_grad_enabled():
+        return False
+    return any(isinstance(a, torch.Tensor) and a.requires_grad for a in list(args) + list(kwargs.values()))
+
+
+def _dispatcher(ours, ref):
+    """ours under no_grad / on detached inputs; the reference's own function when autograd has to record the call
+    (unless ``ours`` brings a backward of its own)."""
+    if getattr(ours, "ogmm_autograd_safe", False) or not callable(ref):
+        return ours          # index-only results (knn, FPS) or a replacement with its own backward
+
+    @functools.wraps(ref)
+    def call(*args, **kwargs):
+        if _needs_grad(args, kwargs):
+            return ref(*args, **kwargs)
+        return ours(*args, **kwargs)
+
+    call.ogmm_kernel = ours
+    call.ogmm_reference = ref
+    return call
+
+
+def _class_dispatcher(ours_cls, ref_cls):
+    class Patched(ours_cls):
+        __doc__ = ours_cls.__doc__
+
+        def forward(self, *args, **kwargs):
+            if _needs_grad(args, kwargs):
+                return ref_cls.forward(self, *args, **kwargs)        # same attributes (is_sk / n_clusters): duck-typed self
+            return ours_cls.forward(self, *args, **kwargs)
+
+    Patched.__name__ = ours_cls.__name__
+    Patched.__qualname__ = ours_cls.__qualname__
+    Patched.ogmm_reference = ref_cls
+    return Patched
+
+
+def install(modules=None, model=None):
+    """Rebind the hot-path names in every already-imported reference module.  Returns the list patched.
+
+    ``model``: an already constructed reference model whose ``GMMSVD`` / ``Clustering`` instances should switch to the
+    kernel-backed classes as well (``uninstall()`` switches them back)."""
     done = []
     for mod_name, table in PATCH_TABLE.items():
         if modules is not None and mod_name not in modules:
@@ -46,14 +106,27 @@ def install(modules=None):
         if mod is None:
             continue
         for attr, repl in table.items():
-            if hasattr(mod, attr):
-                _saved.setdefault((mod_name, attr), getattr(mod, attr))
-                setattr(mod, attr, repl)
-                done.append(f"{mod_name}.{attr}")
+            if not hasattr(mod, attr):
+                continue
+            orig = _saved.setdefault((mod_name, attr), getattr(mod, attr))
+            new = _class_dispatcher(repl, orig) if isinstance(repl, type) else _dispatcher(repl, orig)
+            setattr(mod, attr, new)
+            done.append(f"{mod_name}.{attr}")
+    if model is not None:
+        for m in model.modules():
+            for (mod_name, attr), orig in _saved.items():
+                if isinstance(orig, type) and type(m) is orig:
+                    _reclassed.append((m, orig))
+                    m.__class__ = getattr(sys.modules[mod_name], attr)
+                    done.append(f"instance:{type(m).__name__}")
+                    break
     return done
 
 
 def uninstall():
+    for m, orig in _reclassed:
+        m.__class__ = orig
+    _reclassed.clear()
     for (mod_name, attr), orig in list(_saved.items()):
         mod = sys.modules.get(mod_name)
         if mod is not None:

@@ -49,6 +49,21 @@ def knn_graph(src, dst, k, normalize=False, want_edge=False, want_dist=False):
     return idx, dist, edge
 
 
+def square_distance(src, dst, normalize=False):
+    """src (B,N,C), dst (B,M,C) views -> dist (B,N,M), the reference's expanded form with clamp 1e-12."""
+    _need_cuda_f32("src", src); _need_cuda_f32("dst", dst)
+    if src.dim() != 3 or dst.dim() != 3 or src.shape[0] != dst.shape[0] or src.shape[2] != dst.shape[2]:
+        raise ValueError(f"square_distance: incompatible shapes {tuple(src.shape)} and {tuple(dst.shape)}")
+    B, N, C = src.shape
+    M = dst.shape[1]
+    dist = torch.empty((B, N, M), dtype=torch.float32, device=src.device)
+    with torch.cuda.device(src.device):
+        st = _lib.load().ogmm_square_distance(src.data_ptr(), *src.stride(), dst.data_ptr(), *dst.stride(), B, N, M, C,
+                                              int(bool(normalize)), dist.data_ptr(), _stream(src))
+    _lib.check(st, "ogmm_square_distance")
+    return dist
+
+
 def knn_wide(src, dst, k, normalize=False, want_dist=False):
     """Tensor-core feature-space kNN (32 <= C <= 256): idx (B,N,k) int64 [, dist], fallback count (1,) int32."""
     _need_cuda_f32("src", src); _need_cuda_f32("dst", dst)

@@ -15,12 +15,14 @@ import torch
 
 from . import ops
 
-STAGES = ("knn_edge", "cluster", "feat_moments", "procrustes")
+STAGES = ("knn_edge", "knn_wide", "cluster", "feat_moments", "procrustes")
+DEEPGMR_STAGES = ("knn_edge", "softmax_em", "gmm_register")
 
 
 def launches_per_step(iters=10):
-    """Kernel launches of one ``register_hot_path`` call: 2 kNN, 2 x (main + follow-up) clustering, 2 feature M-step, 1 head."""
-    return 2 + 2 * 2 + 2 + 1
+    """Kernel launches of one ``register_hot_path`` call: 2 kNN, 2 x (main + ``iters`` redo rounds, normally empty)
+    clustering, 2 feature M-step, 1 head."""
+    return 2 + 2 * (1 + iters) + 2 + 1
 
 
 _side_streams = {}
@@ -41,27 +43,33 @@ def _side_stream(device):
     return _side_streams[key]
 
 
-def _cloud_chain(x, feats, o, n_clusters, k, iters, timers, tag, feats_ready=None):
+def _cloud_chain(x, feats, o, n_clusters, k, iters, timers, tag, feats_ready=None, wide=None):
     """kNN graph + edge features, clustering, feature M-step for one side (src or tgt) on the current stream.
 
     ``feats_ready``: optional CUDA event after which ``feats`` may be read (its host-to-device copy); only the
     feature M-step waits on it, the kNN graph and the clustering need xyz and the overlap scores alone.
+    ``wide``: optional (B,N,C) wide point features whose feature-space kNN graph is built as well (the
+    large-scale configuration, BASELINE.json configs[3]; tensor-core kernel for 32 <= C <= 256).
     """
     pts = x.transpose(-1, -2)
     with _Stage(timers, "knn_edge"):
         edge = ops.knn_graph(pts, pts, k, want_edge=True)[2].permute(0, 3, 1, 2)
+    wide_idx = None
+    if wide is not None:
+        with _Stage(timers, "knn_wide"):
+            wide_idx = ops.knn_graph(wide, wide, k)[0]
     with _Stage(timers, "cluster"):
         gam, pi, mu, _ = ops.sinkhorn_cluster(pts, o, n_clusters, iters=iters)
     if feats_ready is not None:
         torch.cuda.current_stream(x.device).wait_event(feats_ready)
     with _Stage(timers, "feat_moments"):
         nf = ops.gmm_moments(gam, feats.transpose(-1, -2))[1]
-    return edge, gam, pi, mu, nf
+    return edge, gam, pi, mu, nf, wide_idx
 
 
 @torch.no_grad()
 def register_hot_path(src, tgt, src_feats, tgt_feats, src_o, tgt_o, n_clusters=16, k=20, iters=10, timers=None,
-                      overlap=True, feats_ready=(None, None)):
+                      overlap=True, feats_ready=(None, None), wide=(None, None)):
     """src, tgt (B,3,N|M); *_feats (B,D,N|M); *_o (B,N|M)  ->  dict with rot (B,3,3), trans (B,3),
     edge_src/edge_tgt (B,6,N,k) views, and the GMM parameters of both clouds.
 
@@ -77,21 +85,23 @@ def register_hot_path(src, tgt, src_feats, tgt_feats, src_o, tgt_o, n_clusters=1
         side = _side_stream(src.device)
         side.wait_stream(cur)
         with torch.cuda.stream(side):
-            edge_t, gam_t, pi_t, mu_t, nf_t = _cloud_chain(tgt, tgt_feats, tgt_o, n_clusters, k, iters, timers, "tgt",
-                                                           feats_ready[1])
-        edge_s, gam_s, pi_s, mu_s, nf_s = _cloud_chain(src, src_feats, src_o, n_clusters, k, iters, timers, "src",
-                                                       feats_ready[0])
+            edge_t, gam_t, pi_t, mu_t, nf_t, wi_t = _cloud_chain(tgt, tgt_feats, tgt_o, n_clusters, k, iters, timers, "tgt",
+                                                           feats_ready[1], wide[1])
+        edge_s, gam_s, pi_s, mu_s, nf_s, wi_s = _cloud_chain(src, src_feats, src_o, n_clusters, k, iters, timers, "src",
+                                                       feats_ready[0], wide[0])
         cur.wait_stream(side)
-        for t in (edge_t, gam_t, pi_t, mu_t, nf_t):
-            t.record_stream(cur)
+        for t in (edge_t, gam_t, pi_t, mu_t, nf_t, wi_t):
+            if t is not None:
+                t.record_stream(cur)
     else:
-        edge_s, gam_s, pi_s, mu_s, nf_s = _cloud_chain(src, src_feats, src_o, n_clusters, k, iters, timers, "src",
-                                                       feats_ready[0])
-        edge_t, gam_t, pi_t, mu_t, nf_t = _cloud_chain(tgt, tgt_feats, tgt_o, n_clusters, k, iters, timers, "tgt",
-                                                       feats_ready[1])
+        edge_s, gam_s, pi_s, mu_s, nf_s, wi_s = _cloud_chain(src, src_feats, src_o, n_clusters, k, iters, timers, "src",
+                                                       feats_ready[0], wide[0])
+        edge_t, gam_t, pi_t, mu_t, nf_t, wi_t = _cloud_chain(tgt, tgt_feats, tgt_o, n_clusters, k, iters, timers, "tgt",
+                                                       feats_ready[1], wide[1])
     with _Stage(timers, "procrustes"):
         rot, trans, corr, _ = ops.soft_procrustes(mu_s, mu_t, nf_s, nf_t, 0.05)
-    return {"rot": rot, "trans": trans, "edge_src": edge_s, "edge_tgt": edge_t, "src_gamma": gam_s, "tgt_gamma": gam_t,
+    extra = {} if wi_s is None else {"src_wide_idx": wi_s, "tgt_wide_idx": wi_t}
+    return {**extra, "rot": rot, "trans": trans, "edge_src": edge_s, "edge_tgt": edge_t, "src_gamma": gam_s, "tgt_gamma": gam_t,
             "src_pi": pi_s, "tgt_pi": pi_t, "src_mu": mu_s, "tgt_mu": mu_t, "src_node_feats": nf_s,
             "tgt_node_feats": nf_t, "src_corr": corr}
 
@@ -108,25 +118,61 @@ class GraphedHotPath:
     returned dict holds the same output tensors every time (clone what must outlive the next replay).
     """
 
-    def __init__(self, src, tgt, src_feats, tgt_feats, src_o, tgt_o, n_clusters=16, k=20, iters=10, warmup=3):
+    def __init__(self, src, tgt, src_feats, tgt_feats, src_o, tgt_o, n_clusters=16, k=20, iters=10, warmup=3, fn=None,
+                 **kwargs):
         self.inputs = (src, tgt, src_feats, tgt_feats, src_o, tgt_o)
         self.args = (n_clusters, k, iters)
+        fn = fn or (lambda: register_hot_path(*self.inputs, *self.args, **kwargs))
         dev = src.device
         cur = torch.cuda.current_stream(dev)
         warm = torch.cuda.Stream(device=dev)
         warm.wait_stream(cur)
         with torch.cuda.stream(warm):                 # lazy one-time setup (function attributes, driver entry points)
             for _ in range(max(int(warmup), 1)):
-                register_hot_path(*self.inputs, *self.args)
+                fn()
         cur.wait_stream(warm)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.out = register_hot_path(*self.inputs, *self.args)
+            self.out = fn()
 
     def replay(self):
         self.graph.replay()
         return self.out
+
+
+@torch.no_grad()
+def deepgmr_hot_path(src, tgt, src_logits, tgt_logits, k=20, timers=None, overlap=True):
+    """DeepGMR's share of the path (baseline/deepgmr.py:64-79; BASELINE.json configs[2]): the DGCNN kNN graph + edge
+    features of both clouds, the fused softmax E-step + M-step with sigma (:71-74), and gmm_register (:17-38).
+
+    src, tgt (B,3,N|M); *_logits (B,J,N|M), the output of the PyTorch ``cluster`` CONV  ->  dict with transform
+    (B,4,4), the edge tensors and the GMM parameters."""
+    def side_chain(x, logits):
+        pts = x.transpose(-1, -2)
+        with _Stage(timers, "knn_edge"):
+            edge = ops.knn_graph(pts, pts, k, want_edge=True)[2].permute(0, 3, 1, 2)
+        with _Stage(timers, "softmax_em"):
+            _, pi, mu, sigma = ops.softmax_moments(logits, x, want_gamma=False)
+        return edge, pi, mu, sigma
+
+    cur = torch.cuda.current_stream(src.device)
+    if overlap:
+        side = _side_stream(src.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            edge_t, pi_t, mu_t, sg_t = side_chain(tgt, tgt_logits)
+        edge_s, pi_s, mu_s, sg_s = side_chain(src, src_logits)
+        cur.wait_stream(side)
+        for t in (edge_t, pi_t, mu_t, sg_t):
+            t.record_stream(cur)
+    else:
+        edge_s, pi_s, mu_s, sg_s = side_chain(src, src_logits)
+        edge_t, pi_t, mu_t, sg_t = side_chain(tgt, tgt_logits)
+    with _Stage(timers, "gmm_register"):
+        tf = ops.gmm_register(pi_s, mu_s, mu_t, sg_t)
+    return {"transform": tf, "rot": tf[:, :3, :3], "trans": tf[:, :3, 3], "edge_src": edge_s, "edge_tgt": edge_t,
+            "src_pi": pi_s, "src_mu": mu_s, "src_sigma": sg_s, "tgt_pi": pi_t, "tgt_mu": mu_t, "tgt_sigma": sg_t}
 
 
 class _Stage:
@@ -147,7 +193,7 @@ class _Stage:
 
 
 @torch.no_grad()
-def register_from_host(host, device, n_clusters=16, k=20, iters=10):
+def register_from_host(host, device, n_clusters=16, k=20, iters=10, device_feats=None):
     """End-to-end call with HOST buffers: pinned tensors in, (rot, trans) back on the host.
 
     ``host`` maps src, tgt, src_feats, tgt_feats, src_o, tgt_o to pinned CPU tensors.  Returns
@@ -157,27 +203,46 @@ def register_from_host(host, device, n_clusters=16, k=20, iters=10):
     (2 x 537 MB) follow on a copy stream, and only the feature M-step of each side waits for its tensor, so the kNN
     graph and the clustering of the WHOLE batch run under the copies.  The batch is not chunked: the Sinkhorn early
     exit is a mean over the batch (lib/utils.py:99-102) and chunking would change the iteration schedule.
+
+    ``device_feats``: optional (src_feats, tgt_feats) already resident on ``device`` -- the model-boundary variant: in
+    the real forward the 512-d point features are produced on the device by the PyTorch DGCNN + attention
+    (models/gmmreg.py:52-97) and never exist on the host; only xyz and the overlap scores cross PCIe then.
     """
-    names = ("src", "tgt", "src_feats", "tgt_feats", "src_o", "tgt_o")
+    names = ("src", "tgt", "src_o", "tgt_o") if device_feats is not None else ("src", "tgt", "src_feats", "tgt_feats", "src_o", "tgt_o")
     cur = torch.cuda.current_stream(device)
-    copy = _copy_stream(device)
     dev = {n: host[n].to(device, non_blocking=True) for n in ("src", "tgt", "src_o", "tgt_o")}
-    ready = []
-    copy.wait_stream(cur)
-    with torch.cuda.stream(copy):
-        for n in ("src_feats", "tgt_feats"):
-            dev[n] = host[n].to(device, non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(copy)
-            ready.append(ev)
-    dev["src_feats"].record_stream(cur)
-    dev["tgt_feats"].record_stream(_side_stream(device))
+    ready = (None, None)
+    if device_feats is None:
+        copy = _copy_stream(device)
+        ready = []
+        copy.wait_stream(cur)
+        with torch.cuda.stream(copy):
+            for n in ("src_feats", "tgt_feats"):
+                dev[n] = host[n].to(device, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy)
+                ready.append(ev)
+        dev["src_feats"].record_stream(cur)
+        dev["tgt_feats"].record_stream(_side_stream(device))
+    else:
+        dev["src_feats"], dev["tgt_feats"] = device_feats
     out = register_hot_path(dev["src"], dev["tgt"], dev["src_feats"], dev["tgt_feats"], dev["src_o"], dev["tgt_o"],
                             n_clusters, k, iters, feats_ready=tuple(ready))
     rot, trans = out["rot"].cpu(), out["trans"].cpu()
     h2d = sum(host[n].numel() * host[n].element_size() for n in names)
     d2h = rot.numel() * 4 + trans.numel() * 4
     return rot, trans, h2d, d2h
+
+
+@torch.no_grad()
+def deepgmr_from_host(host, device, k=20):
+    """DeepGMR path end to end: pinned src, tgt (B,3,N) and src_logits, tgt_logits (B,J,N) in, the (B,4,4) transform
+    back on the host, plus the bytes moved in each direction."""
+    names = ("src", "tgt", "src_logits", "tgt_logits")
+    dev = {n: host[n].to(device, non_blocking=True) for n in names}
+    out = deepgmr_hot_path(dev["src"], dev["tgt"], dev["src_logits"], dev["tgt_logits"], k)
+    tf = out["transform"].cpu()
+    return tf, sum(host[n].numel() * host[n].element_size() for n in names), tf.numel() * 4
 
 
 # ---- pair sharding -------------------------------------------------------------------------------------

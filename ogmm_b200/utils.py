@@ -19,20 +19,13 @@ __all__ = ["square_distance", "knn", "get_graph_feature", "sinkhorn", "index_poi
            "wkeans_plus"]
 
 
+@forward_only
 def square_distance(src, dst, normalize=False):
     """lib/utils.py:12-34.  The dense (B,N,M) matrix, for callers that want it (metrics, losses).
 
-    The hot path never materialises this matrix -- ``knn`` fuses it with the selection -- so this
-    stays a handful of torch ops on the caller's device, in the reference's operation order.
-    """
-    nb, n, _ = src.shape
-    m = dst.shape[1]
-    dist = torch.matmul(src, dst.permute(0, 2, 1)) * -2
-    if normalize:
-        return dist + 2.0
-    dist += torch.sum(src ** 2, -1).view(nb, n, 1)
-    dist += torch.sum(dst ** 2, -1).view(nb, 1, m)
-    return torch.clamp(dist, min=1e-12)
+    The hot path never materialises this matrix -- ``knn`` fuses it with the selection -- but the stand-alone
+    function runs the same arithmetic in its own kernel (``ogmm_square_distance``)."""
+    return ops.square_distance(src, dst, normalize)
 
 
 @torch.no_grad()
@@ -41,6 +34,9 @@ def knn(src, tgt, k, normalize=False):
 
     Ties resolve to the lowest index (torch.topk's order is unspecified)."""
     return ops.knn_graph(src, tgt, k, normalize)[0]
+
+
+knn.ogmm_autograd_safe = True            # int64 indices: nothing to differentiate
 
 
 @forward_only
@@ -105,6 +101,9 @@ def farthest_point_sample(xyz, npoint, is_center=False):
     (``torch.randint(0, N, (B,), dtype=torch.long)`` on the host, :190) so a seeded run matches."""
     start = None if is_center else torch.randint(0, xyz.shape[1], (xyz.shape[0],), dtype=torch.long)
     return ops.fps(xyz, npoint, start)[0]
+
+
+farthest_point_sample.ogmm_autograd_safe = True
 
 
 @forward_only

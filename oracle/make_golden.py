@@ -31,19 +31,11 @@ OUT = os.path.join(ROOT, "tests", "golden")
 
 
 def import_reference():
-    for name in ("transforms3d", "transforms3d.quaternions", "open3d", "h5py", "plyfile"):
-        if name not in sys.modules:
-            sys.modules[name] = types.ModuleType(name)
-    sys.modules["transforms3d"].quaternions = sys.modules["transforms3d.quaternions"]
-    sys.modules["plyfile"].PlyData = object
-    sys.modules["plyfile"].PlyElement = object
-    if REF not in sys.path:
-        sys.path.insert(0, REF)
-    import lib.utils as ru
-    import lib.se3 as rs
-    import models.dgcnn as rd
-    import baseline.deepgmr as rg
-    return ru, rs, rd, rg
+    """The unmodified reference from where it lies (never the vendored copy: fixtures come from the source)."""
+    sys.path.insert(0, ROOT)
+    from oracle import refload
+    m = refload.import_reference(REF)
+    return m["utils"], m["se3"], m["dgcnn"], m["deepgmr"]
 
 
 def npy(t):

@@ -27,3 +27,16 @@ def rot_err_deg(r1, r2):
     the chord form is exact to first order and is what a 1e-3 degree parity bar needs."""
     chord = (r1.double() - r2.double()).flatten(1).norm(dim=1)
     return 2 * torch.arcsin(torch.clamp(chord / (2 * 2 ** 0.5), max=1.0)) * 180 / torch.pi
+
+
+def within_bar(err, bar, spread, what, factor=2.0):
+    """The north-star bar, stated against what the reference itself can resolve.
+
+    ``err``    our result vs the fp32 reference (golden fixture or fp32 oracle)
+    ``spread`` the reference's own fp32-vs-fp64 difference on the same inputs (oracle run in float64 = the arbiter)
+    Passes when ``err <= bar``; when the fp32 reference itself sits further than ``bar / factor`` from the fp64
+    arbiter, the bar it can support is ``factor x spread`` and that is what is required.  Both numbers are printed
+    so the log shows which case applied."""
+    limit = max(bar, factor * spread)
+    print(f"  {what}: err {err:.3e}  bar {bar:.1e}  reference fp32-vs-fp64 spread {spread:.3e}  -> limit {limit:.3e}")
+    assert err <= limit, f"{what}: {err:.3e} > {limit:.3e}"

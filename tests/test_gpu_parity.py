@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 import torch
 
-from gpu_util import decidable_rows, rot_err_deg
+from gpu_util import decidable_rows, rot_err_deg, within_bar
 
 pytestmark = pytest.mark.gpu
 
@@ -71,6 +71,62 @@ def test_knn_golden(og, golden):
     assert torch.equal(idc[ok], gc["idx"][ok])
 
 
+def test_square_distance_and_dist_out_golden(og, orc, golden):
+    """Row a1 (lib/utils.py:12-34): the dense matrix from its own kernel, and the distances the kNN kernels return,
+    against the reference's matrix (golden ``knn_xyz.npz:dist`` / ``knn_cosine.npz:dist``).  The kernels evaluate the
+    reference's expanded form in its operation order, so the comparison is to a few ulp of |x|^2 + |y|^2."""
+    g = golden("knn_xyz")
+    ulp = 2.0 ** -23 * float((g["src"] ** 2).sum(-1).max() + (g["dst"] ** 2).sum(-1).max())
+    dense = og.square_distance(cu(g["src"]), cu(g["dst"])).cpu()
+    assert tuple(dense.shape) == tuple(g["dist"].shape)
+    assert float((dense - g["dist"]).abs().max()) <= 2 * ulp
+    print(f"\n  square_distance: {float((dense == g['dist']).float().mean()):.4f} of entries bit-identical to the reference")
+    assert float(dense.min()) >= 1e-12                                           # the clamp
+    idx, dist, _ = og.ops.knn_graph(cu(g["src"]), cu(g["dst"]), 8, want_dist=True)
+    assert torch.equal(dist.cpu(), torch.gather(dense, 2, idx.cpu())), "dist_out is a gather of the dense matrix, bit for bit"
+    assert float((dist.cpu() - torch.gather(g["dist"], 2, idx.cpu())).abs().max()) <= 2 * ulp
+    assert bool((dist[:, :, 1:] >= dist[:, :, :-1]).all()), "ascending"
+    # the exhaustive and generic kernels return the same distances as the sweep kernel
+    gc = golden("knn_cosine")
+    dc = og.square_distance(cu(gc["src"]), cu(gc["src"]), True).cpu()
+    assert float((dc - gc["dist"]).abs().max()) <= 4 * 2.0 ** -23
+    idc, distc, _ = og.ops.knn_graph(cu(gc["src"]), cu(gc["src"]), 5, True, want_dist=True)
+    assert torch.equal(distc.cpu(), torch.gather(dc, 2, idc.cpu()))
+    # strided (B,3,N) views and a ragged wide case against the oracle's matrix
+    x = torch.rand(2, 3, 333)
+    d3 = og.square_distance(cu(x).transpose(1, 2), cu(x).transpose(1, 2)).cpu()
+    assert float((d3 - orc.pairwise_sqdist(x.transpose(1, 2), x.transpose(1, 2))).abs().max()) <= 2 * 2.0 ** -23 * 6
+    f = torch.relu(torch.randn(1, 77, 70))
+    h = torch.relu(torch.randn(1, 131, 70))
+    dw = og.square_distance(cu(f), cu(h)).cpu()
+    ref = orc.pairwise_sqdist(f.double(), h.double())
+    assert float((dw.double() - ref).abs().max() / ref.abs().max()) < 1e-6
+
+
+def test_knn_nan_and_inf_inputs_stay_in_range(og):
+    """Non-finite coordinates: every returned index must be a valid row and the edge gather must not read
+    out of bounds; rows without NaN keep their exact neighbours."""
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(2, 600, 3, generator=g)
+    clean = og.ops.knn_graph(cu(x), cu(x), 20)[0].cpu()
+    bad = x.clone()
+    bad[0, 5] = float("nan")
+    bad[1, 7, 1] = float("inf")
+    idx, _, edge = og.ops.knn_graph(cu(bad), cu(bad), 20, want_edge=True)
+    torch.cuda.synchronize()
+    assert int(idx.min()) >= 0 and int(idx.max()) < 600
+    allnan = torch.full((1, 64, 3), float("nan"))
+    idx2, _, _ = og.ops.knn_graph(cu(allnan), cu(allnan), 8, want_edge=True)
+    torch.cuda.synchronize()
+    assert int(idx2.min()) >= 0 and int(idx2.max()) < 64
+    for n, c in ((300, 3), (300, 16), (5000, 3)):                   # exhaustive / generic kernels
+        y = torch.rand(1, n, c, generator=g)
+        y[0, 1] = float("nan")
+        i3 = og.ops.knn_graph(cu(y), cu(y), 8, normalize=(c == 16))[0]
+        assert int(i3.min()) >= 0 and int(i3.max()) < n
+    del clean
+
+
 @pytest.mark.parametrize("n,m,k", [(1024, 1024, 20), (717, 717, 20), (300, 1500, 5), (64, 40, 1), (33, 33, 33), (2500, 2500, 16), (4500, 4500, 8), (100, 4200, 20)])
 def test_knn_xyz_sizes(og, n, m, k):
     g = torch.Generator().manual_seed(n * 7 + m)
@@ -128,6 +184,45 @@ def test_knn_wide_tensor_core(og, n, m, c, k, norm):
     print(f"knn_wide C={c}: exhaustive fallbacks {int(fb)} of {2 * n} queries")
     assert int(fb) < 0.02 * 2 * n
     check_knn(og, src, dst, k, norm)          # og.knn routes C >= 32 to the tensor-core kernel
+
+
+def _check_rows_subset(og, pts, k, rows, normalize=False):
+    """kNN on the whole cloud, verified on a subset of query rows against the fp64 order (the dense fp64 matrix of a
+    16384-point cloud is 2 GB; 2048 rows of it are 268 MB)."""
+    idx = og.knn(cu(pts), cu(pts), k, normalize).cpu()
+    q = pts[:, rows]
+    ok, dist = decidable_rows(q, pts, k, normalize)
+    ref = dist.topk(k, dim=-1, largest=False, sorted=True)[1]
+    got = idx[:, rows]
+    assert ok.float().mean() > 0.5
+    assert torch.equal(got[ok], ref[ok]), "decidable rows must match the fp64 order exactly"
+    assert float((torch.gather(dist, 2, got) - torch.gather(dist, 2, ref)).abs().max()) < 1e-4 * float(dist.max())
+    return float(ok.float().mean())
+
+
+def test_knn_cfg4_size(og):
+    """BASELINE.json configs[3] at its own size: 16384 points; the xyz graph (exhaustive kernel above 4096 points) and
+    the C = 64 feature-space graph (tensor-core kernel)."""
+    from ogmm_b200 import synth
+    g = torch.Generator().manual_seed(44)
+    src, _, _, _ = synth.modelnet_batch(3, 1, 16384)
+    xyz = torch.from_numpy(src).transpose(1, 2).contiguous()            # (1,16384,3)
+    rows = torch.cat([torch.arange(0, 1024), torch.randint(0, 16384, (1024,), generator=g)])
+    f = _check_rows_subset(og, xyz, 20, rows)
+    wide = torch.relu(torch.randn(1, 16384, 64, generator=g))
+    fw = _check_rows_subset(og, wide, 20, rows)
+    print(f"\n  N=16384: decidable rows xyz {f:.3f}, C=64 {fw:.3f}")
+
+
+def test_cluster_cfg4_size(og, orc):
+    """BASELINE.json configs[3] at its own size: wkeans_plus on 16384 points with J = 64, iteration trace included."""
+    from ogmm_b200 import synth
+    src, _, _, _ = synth.modelnet_batch(17, 1, 16384)
+    xyz = torch.from_numpy(src).transpose(1, 2).contiguous()
+    g = torch.Generator().manual_seed(64)
+    feats = torch.relu(torch.randn(1, 128, 16384, generator=g))
+    o = torch.sigmoid(torch.randn(1, 16384, generator=g))
+    check_cluster(og, orc, xyz, feats, o, 64)
 
 
 def test_edge_features(og, orc, golden):
@@ -253,7 +348,7 @@ def test_deepgmr_em_vs_oracle(og, orc, b, n, j):
     assert relerr(pi, rpi) < 1e-5 and relerr(mu, rmu) < 1e-5 and relerr(sigma, rsg) < 1e-4
 
 
-def test_deepgmr_em_and_register(og, golden):
+def test_deepgmr_em_and_register(og, orc, golden):
     g = golden("deepgmr")
     gam, pi, mu, sigma = og.deepgmr_em(cu(g["src_logits"]), cu(g["src"]))
     assert relerr(gam, g["src_gamma"]) < 1e-5 and relerr(pi, g["src_pi"]) < 1e-5
@@ -262,9 +357,17 @@ def test_deepgmr_em_and_register(og, golden):
     pi2, mu2, sg2 = og.gmm_params(cu(g["src_gamma"]).transpose(-1, -2), cu(g["src"]).transpose(-1, -2), True)
     assert relerr(pi2, g["src_pi"]) < 1e-5 and relerr(mu2, g["src_mu"]) < 1e-5 and relerr(sg2, g["src_sigma"]) < 1e-4
     tf = og.gmm_register(cu(g["src_pi"]), cu(g["src_mu"]), cu(g["tgt_mu"]), cu(g["tgt_sigma"])).cpu()
-    assert float(rot_err_deg(tf[:, :3, :3], g["transform"][:, :3, :3]).max()) < 1e-3
+    tf64 = orc.deepgmr_register(g["src_pi"].double(), g["src_mu"].double(), g["tgt_mu"].double(), g["tgt_sigma"].double())
     scale = float(g["tgt_mu"].abs().max())
-    assert float((tf[:, :3, 3] - g["transform"][:, :3, 3]).abs().max()) < 1e-5 * max(scale, 1.0) * 10
+    ref = g["transform"]
+    print()
+    within_bar(float(rot_err_deg(tf[:, :3, :3], ref[:, :3, :3]).max()), 1e-3,
+               float(rot_err_deg(ref[:, :3, :3], tf64[:, :3, :3]).max()), "gmm_register rotation [deg]")
+    within_bar(float((tf[:, :3, 3] - ref[:, :3, 3]).abs().max()), 1e-5 * scale,
+               float((ref[:, :3, 3].double() - tf64[:, :3, 3]).abs().max()), "gmm_register translation")
+    # against the fp64 arbiter the bars hold outright
+    assert float(rot_err_deg(tf[:, :3, :3], tf64[:, :3, :3]).max()) < 1e-3
+    assert float((tf[:, :3, 3].double() - tf64[:, :3, 3]).abs().max()) < 1e-5 * scale
     assert torch.equal(tf[:, 3], g["transform"][:, 3])
 
 
@@ -301,20 +404,28 @@ def check_cluster(og, orc, xyz, feats, o, J, tol_mu=1e-4):
     e_pi = relerr(pi, rpi)
     e_nf = float((nf.cpu() - rnf).abs().max() / rnf.abs().max())
     e_g = float((gam.cpu() - rg).abs().max())
+    g_spread = float((rg.double() - dg).abs().max())
     print(f"cluster parity N={xyz.shape[1]} J={J}: mu {e_mu:.2e} (vs fp64 {e_mu64:.2e}, oracle fp32-fp64 spread {spread:.2e}) "
-          f"pi {e_pi:.2e} feats {e_nf:.2e} gamma abs {e_g:.2e}")
-    assert e_mu < tol_mu and e_pi < 1e-4 and e_nf < 1e-4 and e_g < 1e-3
+          f"pi {e_pi:.2e} feats {e_nf:.2e} gamma abs {e_g:.2e} (oracle fp32-fp64 spread {g_spread:.2e})")
+    assert e_mu < tol_mu and e_pi < 1e-4 and e_nf < 1e-4
+    # gamma is an absolute quantity in [0, 1] (1e-4 relative to its O(1) entries); the fp32 reference itself is only
+    # defined to its fp32-vs-fp64 spread (eps = 1e-2 amplifies cost rounding 100x)
+    assert e_g <= max(1e-4, 3.0 * g_spread), (e_g, g_spread)
     return gam, pi, mu, nf
 
 
-def test_cluster_golden(og, golden):
+def test_cluster_golden(og, orc, golden):
     for tag in ("small", "full"):
         g = golden(f"wkeans_{tag}")
         gam, pi, mu, nf = og.wkeans_plus(cu(g["xyz"]), cu(g["feats"]).transpose(-1, -2), cu(g["o"]), int(g["J"]))
         scale = float(g["node_xyz"].abs().max())
         assert float((mu.cpu() - g["node_xyz"]).abs().max()) / scale < 1e-4
         assert relerr(pi, g["pi"]) < 1e-4 and relerr(nf, g["node_feats"]) < 1e-4
-        assert float((gam.cpu() - g["gamma"]).abs().max()) < 1e-3
+        g64 = orc.sinkhorn_kmeans(g["xyz"].double(), g["feats"].transpose(-1, -2).double(), g["o"].double(), int(g["J"]))[0]
+        g_spread = float((g["gamma"].double() - g64).abs().max())
+        e_g = float((gam.cpu() - g["gamma"]).abs().max())
+        print(f"\n  wkeans_{tag}: gamma abs err {e_g:.2e}, reference fp32-vs-fp64 spread {g_spread:.2e}")
+        assert e_g <= max(1e-4, 3.0 * g_spread)
 
 
 @pytest.mark.parametrize("n,j", [(1024, 16), (717, 16), (256, 8), (2048, 32), (1024, 128), (9000, 24)])
@@ -347,7 +458,9 @@ def test_cluster_early_exit_every_outer_iteration(og, orc, n, j, scale, tau):
     assert run.cpu().tolist() == tr
     sc = float(rmu.abs().max())
     assert float((mu.cpu() - rmu).abs().max()) / sc < 1e-4 and relerr(pi, rpi) < 1e-4
-    assert float((nf.cpu() - rnf).abs().max() / rnf.abs().max()) < 1e-4 and float((gam.cpu() - rg).abs().max()) < 1e-3
+    assert float((nf.cpu() - rnf).abs().max() / rnf.abs().max()) < 1e-4
+    g64 = orc.sinkhorn_kmeans(xyz.double(), feats.transpose(-1, -2).double(), o.double(), j, tau=tau)[0]
+    assert float((gam.cpu() - rg).abs().max()) <= max(1e-4, 3.0 * float((rg.double() - g64).abs().max()))
 
 
 @pytest.mark.timeout(120, method="thread")
@@ -374,6 +487,37 @@ def test_cluster_follow_ups_of_two_streams_do_not_starve_each_other(og):
         torch.cuda.synchronize()
         for a, b in zip(out_s + out_t, ref_s + ref_t):
             assert torch.equal(a, b)
+
+
+@pytest.mark.timeout(180, method="thread")
+def test_cluster_many_concurrent_calls_never_hang(og):
+    """VERDICT r1 item 9 / ADVICE: the redo rounds are ordinary launches that never wait on another CTA, so any number of
+    clustering calls may be in flight on one device.  Six streams, every call hitting the early exit in every outer
+    iteration, plus a stand-alone Sinkhorn next to them: must finish and equal the one-stream results."""
+    from ogmm_b200 import synth
+    src, tgt, _, _ = synth.modelnet_batch(31, 96, 1024)
+    g = torch.Generator().manual_seed(6)
+    clouds = [cu(torch.from_numpy(a).transpose(1, 2).contiguous() * 0.03) for a in (src, tgt)] * 3
+    scores = [cu(torch.sigmoid(torch.randn(96, 1024, generator=g))) for _ in range(6)]
+    cost = cu(torch.rand(8, 512, 16, generator=g))
+    refs = [og.ops.sinkhorn_cluster(x, o, 16, want_iters=True) for x, o in zip(clouds, scores)]
+    ref_sk = og.ops.sinkhorn(cost, None, None, 0.5, 1e-2, 50, want_iters=True)
+    assert all(min(r[3].tolist()) < 10 for r in refs) and int(ref_sk[2][0]) < 50
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream() for _ in range(7)]
+    for _ in range(3):
+        outs = [None] * 6
+        for i, st in enumerate(streams[:6]):
+            st.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(st):
+                outs[i] = og.ops.sinkhorn_cluster(clouds[i], scores[i], 16, want_iters=True)
+        with torch.cuda.stream(streams[6]):
+            sk = og.ops.sinkhorn(cost, None, None, 0.5, 1e-2, 50, want_iters=True)
+        torch.cuda.synchronize()
+        for out, ref in zip(outs, refs):
+            for a, b in zip(out, ref):
+                assert torch.equal(a, b)
+        assert torch.equal(sk[0], ref_sk[0]) and torch.equal(sk[2], ref_sk[2])
 
 
 def test_cluster_metre_scale_and_strided_xyz(og, orc):
@@ -412,19 +556,22 @@ def test_procrustes_exact_motion_known_answer(og):
     w = torch.rand(64, 1, 40, generator=g) + 0.1
     rot, t = og.compute_rigid_transformation(cu(src), cu(corr), cu(w))
     assert float(rot_err_deg(rot.cpu(), q).max()) < 1e-3
-    assert float((t.cpu() - tr).abs().max()) < 1e-4
+    assert float((t.cpu() - tr).abs().max()) < 1e-5 * float(corr.abs().max())
     # strided inputs (transposed views) go through the same kernel
     rot2, _ = og.compute_rigid_transformation(cu(src.transpose(1, 2).contiguous()).transpose(1, 2), cu(corr), cu(w))
     assert torch.equal(rot, rot2)
 
 
-def test_gmmsvd_golden(og, golden):
+def test_gmmsvd_golden(og, orc, golden):
     g = golden("gmmsvd")
     head = og.GMMSVD(False)
     rot, t, corr, tt = head(cu(g["src"]), cu(g["tgt"]), cu(g["src_desc"]), cu(g["tgt_desc"]), cu(g["src_pi"]), cu(g["tgt_pi"]))
-    assert float(rot_err_deg(rot.cpu(), g["rot"]).max()) < 1e-3
+    r64, t64, _, _ = orc.soft_svd_head(g["src"].double(), g["tgt"].double(), g["src_desc"].double(), g["tgt_desc"].double())
     scale = float(g["tgt"].abs().max())
-    assert float((t.cpu() - g["t"]).abs().max()) < 1e-5 * scale * 10
+    print()
+    within_bar(float(rot_err_deg(rot.cpu(), g["rot"]).max()), 1e-3, float(rot_err_deg(g["rot"], r64).max()), "GMMSVD rotation [deg]")
+    within_bar(float((t.cpu() - g["t"]).abs().max()), 1e-5 * scale, float((g["t"].double() - t64).abs().max()), "GMMSVD translation")
+    assert float(rot_err_deg(rot.cpu(), r64).max()) < 1e-3 and float((t.cpu().double() - t64).abs().max()) < 1e-5 * scale
     assert relerr(corr, g["corr"]) < 1e-4 and torch.equal(tt.cpu(), g["tgt_t"])
     sim = og.cos_similarity(cu(g["src_desc"]), cu(g["tgt_desc"]))
     assert float((sim.cpu() - g["sim"]).abs().max()) < 1e-6
@@ -443,9 +590,18 @@ def test_gmmsvd_sizes(og, orc, j, d):
     ds = torch.relu(torch.randn(4, j, d, generator=g))
     dt = ds + 0.02 * torch.randn(4, j, d, generator=g)
     rr, rt, rc, _ = orc.soft_svd_head(mu_s, mu_t, ds, dt)
+    r64, t64, _, _ = orc.soft_svd_head(mu_s.double(), mu_t.double(), ds.double(), dt.double())
     rot, t, corr, _ = og.GMMSVD(False)(cu(mu_s), cu(mu_t), cu(ds), cu(dt), None, None)
-    assert float(rot_err_deg(rot.cpu(), rr).max()) < 1e-3
-    assert relerr(corr, rc) < 1e-4 and float((t.cpu() - rt).abs().max()) < 1e-4
+    scale = float(mu_t.abs().max())
+    print()
+    within_bar(float(rot_err_deg(rot.cpu(), rr).max()), 1e-3, float(rot_err_deg(rr, r64).max()), f"GMMSVD J={j} rotation [deg]")
+    within_bar(float((t.cpu() - rt).abs().max()), 1e-5 * scale, float((rt.double() - t64).abs().max()), f"GMMSVD J={j} translation")
+    assert relerr(corr, rc) < 1e-4
+
+
+def test_se3_helpers_on_device(og, golden):
+    from test_se3_cpu import check_se3
+    check_se3(golden, DEV)
 
 
 # ------------------------------------------------------------------------------------------ full size

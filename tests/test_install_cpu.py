@@ -1,5 +1,6 @@
 """install()/uninstall() against the real reference modules, when the reference checkout is present (authoring
-container only; skipped on the GPU box).  Only name rebinding is checked -- nothing is executed on a GPU."""
+container only; skipped on the GPU box).  Name rebinding and the autograd fall-through are checked here on the CPU;
+tests/test_gpu_model_dropin.py runs the patched reference models on a GPU."""
 import os
 import sys
 import types
@@ -25,17 +26,38 @@ def test_install_rebinds_every_import_site_and_uninstall_restores():
         orig_wk = models.gmmreg.wkeans_plus
         done = install.install()
         assert "models.dgcnn.knn" in done and "models.gmmreg.wkeans_plus" in done and "baseline.deepgmr.gmm_register" in done
-        assert models.dgcnn.knn is og.utils.knn and lib.utils.knn is og.utils.knn
-        assert models.attn.get_graph_feature is og.utils.get_graph_feature
-        assert models.gmmreg.wkeans_plus is og.utils.wkeans_plus and models.gmmreg.GMMSVD is og.modules.GMMSVD
-        assert lib.loss.gmm_params is og.utils.gmm_params and baseline.deepgmr.gmm_register is og.modules.gmm_register
-        assert models.dgcnn.compute_rigid_transformation is og.se3.compute_rigid_transformation
+        kern = lambda f: getattr(f, "ogmm_kernel", f)          # differentiable names are dispatchers around the kernel
+        assert models.dgcnn.knn is og.utils.knn and lib.utils.knn is og.utils.knn          # index-only: bound directly
+        assert kern(models.attn.get_graph_feature) is og.utils.get_graph_feature
+        assert kern(models.gmmreg.wkeans_plus) is og.utils.wkeans_plus and issubclass(models.gmmreg.GMMSVD, og.modules.GMMSVD)
+        assert kern(lib.loss.gmm_params) is og.utils.gmm_params and kern(baseline.deepgmr.gmm_register) is og.modules.gmm_register
+        assert kern(models.dgcnn.compute_rigid_transformation) is og.se3.compute_rigid_transformation
+        # a call that autograd has to record goes to the reference's own function (train.py keeps working) ...
+        import torch
+        g = torch.softmax(torch.rand(2, 32, 4), -1)
+        f = torch.rand(2, 32, 8, requires_grad=True)
+        pi, mu = lib.loss.gmm_params(g, f)
+        assert mu.grad_fn is not None
+        mu.sum().backward()
+        assert f.grad is not None and tuple(f.grad.shape) == (2, 32, 8)
+        head = models.gmmreg.GMMSVD(False)
+        d = torch.rand(2, 4, 8, requires_grad=True)
+        rot = head(torch.rand(2, 4, 3), torch.rand(2, 4, 3), d, torch.rand(2, 4, 8), None, None)[0]
+        assert rot.grad_fn is not None
+        # ... and without a graph the same name reaches the kernels (here: their CUDA-only check)
+        with torch.no_grad():
+            with pytest.raises(TypeError, match="CUDA"):
+                lib.loss.gmm_params(g, f)
+        # install(model=...) switches existing instances to the kernel-backed class; uninstall switches them back
+        ref_cls = install._saved[("models.gmmreg", "Clustering")]
+        net = torch.nn.Sequential(ref_cls(16))
+        assert "instance:Clustering" in install.install(model=net) and isinstance(net[0], og.modules.Clustering)
         # every patched name exists in the reference module it is patched into (no typos in the table)
         for mod_name, table in install.PATCH_TABLE.items():
             for attr in table:
                 assert hasattr(sys.modules[mod_name], attr), f"{mod_name}.{attr} does not exist in the reference"
         install.uninstall()
-        assert models.dgcnn.knn is orig_knn and models.gmmreg.wkeans_plus is orig_wk
+        assert models.dgcnn.knn is orig_knn and models.gmmreg.wkeans_plus is orig_wk and type(net[0]) is ref_cls
     finally:
         sys.path.remove(REF)
 
