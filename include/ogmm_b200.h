@@ -101,12 +101,13 @@ int ogmm_fps(const float* xyz, int64_t sb, int64_t sn, int64_t sc, int64_t B, in
  * :288).  The final feature M-step (:289) is ogmm_gmm_moments_feat.
  *   xyz (B,N,3) strided view; o_scores (B,N) contiguous.
  *   gamma_out (B,N,J), pi_out (B,J), mu_out (B,J,3) contiguous.
- *   The batch-coupled early exit (:99-102) is reproduced exactly: the main launch records every
- *   cloud's per-iteration change, its last CTA evaluates the batch means, and `iters` ordinary redo
- *   launches queued behind it on the same stream (each an empty launch when nothing has to change, the
- *   common case) re-run from the first outer iteration whose inner count changed until the schedule
- *   stands.  No host synchronisation, no cooperative launch, no grid barrier: no launch waits on another
- *   CTA, so any number of clustering calls may be in flight on one device at the same time.
+ *   The batch-coupled early exit (:99-102) is reproduced exactly: the launch records every cloud's
+ *   per-iteration change and its last CTA evaluates the batch means; only when an exit fires does that
+ *   CTA tail-launch a redo round from the device (CUDA dynamic parallelism), which re-runs from the first
+ *   outer iteration whose inner count changed, and so on until the schedule stands (at most `iters`
+ *   rounds).  One host launch, no host synchronisation, no cooperative launch, no grid barrier: no launch
+ *   waits on another CTA, so any number of clustering calls may be in flight on one device at once, and
+ *   the call can be captured into a CUDA graph.
  *   workspace: device scratch of at least ogmm_sinkhorn_cluster_workspace(...) bytes; contents
  *   need not be initialised.  iters_run_out (optional) (iters) int32: inner iterations per outer. */
 int64_t ogmm_sinkhorn_cluster_workspace(int64_t B, int64_t N, int64_t J, int64_t iters, int64_t max_iter);
@@ -144,6 +145,17 @@ int ogmm_gmm_moments_feat(const float* gamma, int64_t g_sb, int64_t g_sn, int64_
                           const float* feats, int64_t f_sb, int64_t f_sn, int64_t f_sd,
                           int64_t B, int64_t N, int64_t J, int64_t D,
                           float* pi_out, float* mu_out, ogmm_stream_t stream);
+
+/* Backward of ogmm_gmm_moments_feat with respect to the features (the reference reaches it
+ * through autograd from lib/utils.py:289 in train.py:57-75, with gamma detached at lib/utils.py:286):
+ *   grad_feats[b,n,d] = sum_j gamma[b,n,j] * grad_mu[b,j,d] / (pi[b,j] * N + 1e-5)
+ *   gamma (B,N,J) strided view; grad_mu (B,J,D) contiguous; pi (B,J) contiguous (the forward's output);
+ *   grad_feats: strided (strides b,n,d) -- pass the (B,D,N) buffer's strides to get the gradient in the model's native
+ *   feature layout, written with coalesced 16-byte stores. */
+int ogmm_gmm_moments_feat_backward(const float* gamma, int64_t g_sb, int64_t g_sn, int64_t g_sj,
+                                   const float* grad_mu, const float* pi,
+                                   int64_t B, int64_t N, int64_t J, int64_t D,
+                                   float* grad_feats, int64_t o_sb, int64_t o_sn, int64_t o_sd, ogmm_stream_t stream);
 
 /* DeepGMR closed-form E-step fused with the M-step (baseline/deepgmr.py:71-74 + lib/utils.py:130-148).
  *   logits (B,J,N) contiguous; pts (B,3,N)-style strided view (strides b,n,d with D == 3).

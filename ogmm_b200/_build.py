@@ -17,7 +17,10 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libogmm_b200.so")
-SOURCES = ["capi.cu", "knn.cu", "knn_sweep.cu", "knn_wide.cu", "cluster.cu", "cluster_big.cu", "sinkhorn.cu", "moments.cu", "moments_tc.cu", "moments_tma.cu", "procrustes.cu"]
+SOURCES = ["capi.cu", "knn.cu", "knn_sweep.cu", "knn_select.cu", "knn_wide.cu", "cluster.cu", "cluster_big.cu", "sinkhorn.cu", "moments.cu", "moments_tc.cu", "moments_tma.cu", "moments_bwd.cu", "procrustes.cu"]
+# translation units whose kernels launch a follow-up grid from the device (CUDA dynamic parallelism): relocatable
+# device code + the device runtime at link time
+RDC_SOURCES = {"cluster.cu", "cluster_big.cu", "sinkhorn.cu"}
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--extended-lambda", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
@@ -56,7 +59,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
                 and os.path.getmtime(obj) > max(newest_header, os.path.getmtime(os.path.join(CSRC, src)))):
             objs.append(obj)          # up to date
             continue
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *(["-rdc=true"] if src in RDC_SOURCES else []), "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -68,7 +71,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             print(out)
         objs.append(obj)
     tmp = LIB + ".tmp"
-    link = [nvcc, "-shared", "-o", tmp, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
+    link = [nvcc, "-shared", "-o", tmp, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudadevrt"]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")

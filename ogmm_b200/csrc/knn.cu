@@ -429,6 +429,11 @@ int ogmm_launch_knn3_sweep(const float* src, int64_t s_sb, int64_t s_sn, int64_t
                            int64_t B, int64_t N, int64_t M, int64_t k,
                            int64_t* idx_out, float* dist_out, float* edge_out, cudaStream_t s);
 
+int ogmm_launch_knn3_select(const float* src, int64_t s_sb, int64_t s_sn, int64_t s_sc,
+                            const float* dst, int64_t d_sb, int64_t d_sn, int64_t d_sc,
+                            int64_t B, int64_t N, int64_t M, int64_t k,
+                            int64_t* idx_out, float* dist_out, float* edge_out, int32_t* stats, cudaStream_t s);
+
 int ogmm_launch_knn_wide(const float* src, int64_t s_sb, int64_t s_sn, int64_t s_sc,
                          const float* dst, int64_t d_sb, int64_t d_sn, int64_t d_sc,
                          int64_t B, int64_t N, int64_t M, int64_t C, int64_t k, int normalize,
@@ -452,6 +457,13 @@ extern "C" __attribute__((visibility("default"))) int ogmm_knn_graph(const float
     // forces the exhaustive kernel (same results; kept for larger clouds and for A/B timing)
     if (C == 3 && !normalize && N <= 4096 && M <= 4096) {
         const char* force = getenv("OGMM_KNN_EXHAUSTIVE");
+        const char* old_sweep = getenv("OGMM_KNN_SWEEP_INSERT");
+        // threshold-then-collect selection (knn_select.cu) where its group bound is defined: at least k groups of four
+        // candidates with room to spare, k within the revisit budget; OGMM_KNN_SWEEP_INSERT=1 keeps the insert-while-
+        // sweeping kernel for A/B timing (bit-identical results)
+        if (!(force && force[0] == '1') && !(old_sweep && old_sweep[0] == '1') && M >= 256 && k <= 24)
+            return ogmm_launch_knn3_select(src, s_sb, s_sn, s_sc, dst, d_sb, d_sn, d_sc, B, N, M, k, idx_out, dist_out,
+                                           edge_out, nullptr, s);
         if (!(force && force[0] == '1'))
             return ogmm_launch_knn3_sweep(src, s_sb, s_sn, s_sc, dst, d_sb, d_sn, d_sc, B, N, M, k, idx_out, dist_out,
                                           edge_out, s);

@@ -31,16 +31,19 @@
 // through the exit test.  The main launch runs every Sinkhorn call for max_iter iterations and records
 // each cloud's change per (outer, inner) iteration; the last CTA to finish evaluates the batch means in
 // order and, at the first (outer o, inner i) with mean < thresh and i+1 below the count that was run,
-// stores n_inner[o] = i+1 and resume = o.  It is followed by `iters` ordinary REDO launches on the same stream:
-// each one returns at once when the schedule already stands (the common case: resume == iters) and
-// otherwise re-runs every cloud from the centroids saved at the start of outer iteration `resume`, after
-// which its last CTA re-evaluates the means.  A redo round certifies at least one more outer iteration (the
-// re-run of iteration `resume` repeats the first n_inner[resume] recorded iterations exactly), so `iters`
-// rounds always suffice.  No launch ever waits on another CTA: there is no grid barrier and no co-residency
-// requirement, so any number of calls may be in flight on a device (streams, MPS partitions, green contexts).
-// The result is bit-identical to running the exit test inline, and deterministic (fixed-order reductions, no
-// float atomics).
+// stores n_inner[o] = i+1 and resume = o.  Only then does that CTA queue a REDO round itself: a device-side tail
+// launch (CUDA dynamic parallelism, cudaStreamTailLaunch) of the same kernel, which starts after the parent grid has
+// drained and before anything else in the stream, re-runs every cloud from the centroids saved at the start of outer
+// iteration `resume`, re-evaluates the means in its own last CTA and, if the schedule still moves, queues the next
+// round.  A redo round certifies at least one more outer iteration (the re-run of iteration `resume` repeats the
+// first n_inner[resume] recorded iterations exactly), so at most `iters` rounds run.  In the common case -- no exit
+// fires -- the host's single launch is all there is.  No launch ever waits on another CTA: there is no grid barrier
+// and no co-residency requirement, so any number of calls may be in flight on a device (streams, MPS partitions,
+// green contexts), and the chain is captured by CUDA graphs like any kernel.  The result is bit-identical to running
+// the exit test inline, and deterministic (fixed-order reductions, no float atomics).
 #pragma once
+
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -55,7 +58,7 @@ struct ClusterWsLayout {
 __host__ __device__ inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 __host__ __device__ inline ClusterWsLayout cluster_ws_layout(int64_t B, int64_t J, int64_t iters, int64_t max_iter) {
     ClusterWsLayout l;
-    l.state_off = 0;                                         // int32[16]: [0]=resume [1]=done counter [2]=rescues
+    l.state_off = 0;                                         // int32[16]: [0]=resume [1]=done counter [2]=rescues [5]=device-side launch failed
     l.ninner_off = 64;                                       // int32[iters]
     l.means_off = align_up(l.ninner_off + 4 * iters, 256);   // float[iters][max_iter] batch means
     l.diffs_off = align_up(l.means_off + 4 * iters * max_iter, 256);   // float[iters][max_iter][B]
@@ -840,11 +843,11 @@ __device__ __forceinline__ void verify_schedule(const SinkhornParams& P, int res
     __syncthreads();
 }
 
-// mode 0: main launch, one CTA per cloud, every Sinkhorn call runs max_iter iterations.
-// mode 1: redo round: returns at once when the schedule stands, otherwise re-runs from outer iteration state[0]
-//         with the inner counts of n_inner[].
-// In both modes the last CTA to finish evaluates the batch-mean exit test and publishes the next `resume`.
-// (One kernel for both so the cloud body is instantiated once.)
+// mode 0: main launch (from the host), one CTA per cloud, every Sinkhorn call runs max_iter iterations.
+// mode 1: redo round (tail-launched by the previous round's last CTA): re-runs from outer iteration state[0] with the
+//         inner counts of n_inner[].
+// In both modes the last CTA to finish evaluates the batch-mean exit test, publishes the next `resume` and, if the
+// schedule moved, tail-launches the next round.  (One kernel for both so the cloud body is instantiated once.)
 template <int NT, int PPT, bool kCluster, bool kFast, bool kExactJ>
 __global__ void __launch_bounds__(NT, (kFast && NT == 256) ? 2 : 1)
 sinkhorn_kernel(SinkhornParams P, int mode) {
@@ -867,6 +870,12 @@ sinkhorn_kernel(SinkhornParams P, int mode) {
     if (S.misc[5] != 0.f) {
         __threadfence();
         verify_schedule<NT>(P, resume, mode == 0);       // also resets the done counter for the next round
+        if (threadIdx.x == 0 && *reinterpret_cast<volatile int32_t*>(P.state) < P.iters) {
+            unsigned dyn_smem;
+            asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn_smem));
+            sinkhorn_kernel<NT, PPT, kCluster, kFast, kExactJ><<<gridDim.x, NT, dyn_smem, cudaStreamTailLaunch>>>(P, 1);
+            if (cudaGetLastError() != cudaSuccess) atomicExch(&P.state[5], 1);      // surfaced by ogmm_sinkhorn_status (tests)
+        }
     }
 }
 
@@ -902,17 +911,9 @@ static inline int launch_sinkhorn_variant(SinkhornParams P, cudaStream_t s) {
         st = cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(sinkhorn_kernel)");
         if (st != OGMM_OK) return st;
     }
+    // one launch from the host; redo rounds, when the early exit fires, are tail-launched from the device (header comment)
     kern<<<(unsigned)P.B, NT, smem, s>>>(P, 0);
-    st = cuda_status(cudaGetLastError(), "sinkhorn_kernel (main launch)");
-    if (st != OGMM_OK) return st;
-    // Redo rounds (see the header comment): each certifies at least one more outer iteration, `iters` always suffice;
-    // a round whose schedule already stands is an empty launch (every CTA reads one word and returns).
-    for (int r = 0; r < P.iters; ++r) {
-        kern<<<(unsigned)P.B, NT, smem, s>>>(P, 1);
-        st = cuda_status(cudaGetLastError(), "sinkhorn_kernel (redo round)");
-        if (st != OGMM_OK) return st;
-    }
-    return OGMM_OK;
+    return cuda_status(cudaGetLastError(), "sinkhorn_kernel");
 }
 
 template <bool kCluster>
@@ -935,7 +936,13 @@ static inline int launch_sinkhorn(SinkhornParams P, void* workspace, int64_t wor
         if (P.J <= 16 && P.N <= 1024) {
             if (P.N <= 256) return launch_sinkhorn_variant<256, 1, true, true>(P, s);
             if (P.N <= 512) return launch_sinkhorn_variant<256, 2, true, true>(P, s);
-            if (P.J == 16) return launch_sinkhorn_variant<256, 4, true, true, true>(P, s);
+            if (P.J == 16) {
+                // 4 warps x 8 points per thread: the per-warp overheads of an iteration (column butterfly, partial-sum
+                // fold, change tracking) are paid by half as many warps per cloud; OGMM_CLUSTER_NT=256 keeps 8 warps x 4
+                const char* nt = getenv("OGMM_CLUSTER_NT");
+                if (nt && nt[0] == '2') return launch_sinkhorn_variant<256, 4, true, true, true>(P, s);
+                return launch_sinkhorn_variant<128, 8, true, true, true>(P, s);
+            }
             return launch_sinkhorn_variant<256, 4, true, true>(P, s);
         }
     }

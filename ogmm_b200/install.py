@@ -16,8 +16,8 @@ Two things to know:
   autograd is recording and an argument requires grad (``train.py:57-75``: the loss calls ``gmm_params``,
   ``get_local_corrs``; the model differentiates through ``gmm_params(gamma, feats)``, ``GMMSVD`` and
   ``compute_rigid_transformation``) the call goes to the reference's own function that the name held before -- exactly
-  what would have run without ``install()``.  Replacements that carry their own backward (``gmm_params`` on wide
-  features, see ``ogmm_b200/autograd.py``) take those calls themselves.  Under ``torch.no_grad()`` / inference every
+  what would have run without ``install()``.  Replacements that carry their own backward (``wkeans_plus`` and
+  ``gmm_params`` on wide features: the feature M-step, see ``ogmm_b200/autograd.py``) take those calls themselves.  Under ``torch.no_grad()`` / inference every
   call runs on the kernels.
 * **Classes.**  ``models.gmmreg.Clustering`` and ``GMMSVD`` are replaced by subclasses of ``ogmm_b200.modules`` that
   dispatch the same way; they take effect for models constructed AFTER ``install()``.  A model built earlier still
@@ -67,9 +67,11 @@ def _dispatcher(ours, ref):
     if getattr(ours, "ogmm_autograd_safe", False) or not callable(ref):
         return ours          # index-only results (knn, FPS) or a replacement with its own backward
 
+    can = getattr(ours, "ogmm_can_differentiate", None)   # a replacement that differentiates SOME calls says which
+
     @functools.wraps(ref)
     def call(*args, **kwargs):
-        if _needs_grad(args, kwargs):
+        if _needs_grad(args, kwargs) and not (can is not None and can(*args, **kwargs)):
             return ref(*args, **kwargs)
         return ours(*args, **kwargs)
 

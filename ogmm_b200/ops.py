@@ -187,6 +187,25 @@ def gmm_moments(gamma, pts, return_sigma=False):
     return (pi, mu, sigma) if return_sigma else (pi, mu)
 
 
+def gmm_moments_feat_backward(gamma, grad_mu, pi, like):
+    """gamma (B,N,J) view, grad_mu (B,J,D), pi (B,J) -> grad_feats with the shape AND memory layout of ``like`` (B,N,D):
+    for the transposed view of a (B,D,N) tensor the gradient comes back as the same kind of view."""
+    _need_cuda_f32("gamma", gamma); _need_cuda_f32("grad_mu", grad_mu); _need_cuda_f32("pi", pi)
+    B, N, J = gamma.shape
+    D = grad_mu.shape[2]
+    if tuple(grad_mu.shape) != (B, J, D) or tuple(pi.shape) != (B, J) or tuple(like.shape) != (B, N, D):
+        raise ValueError("gmm_moments_feat_backward: inconsistent shapes")
+    grad_mu, pi = grad_mu.contiguous(), pi.contiguous()
+    native = like.stride(1) == 1 and like.stride(2) >= N                  # a transposed view of (B,D,N)
+    out = torch.empty((B, D, N), dtype=torch.float32, device=gamma.device).transpose(1, 2) if native else \
+        torch.empty((B, N, D), dtype=torch.float32, device=gamma.device)
+    with torch.cuda.device(gamma.device):
+        st = _lib.load().ogmm_gmm_moments_feat_backward(gamma.data_ptr(), *gamma.stride(), grad_mu.data_ptr(), pi.data_ptr(),
+                                                        B, N, J, D, out.data_ptr(), *out.stride(), _stream(gamma))
+    _lib.check(st, "ogmm_gmm_moments_feat_backward")
+    return out
+
+
 def softmax_moments(logits, pts, want_gamma=True):
     """logits (B,J,N), pts (B,3,N) view -> gamma (B,J,N) | None, pi (B,J), mu (B,J,3), sigma (B,J,3,3)."""
     _need_cuda_f32("logits", logits); _need_cuda_f32("pts", pts)

@@ -20,9 +20,9 @@ DEEPGMR_STAGES = ("knn_edge", "softmax_em", "gmm_register")
 
 
 def launches_per_step(iters=10):
-    """Kernel launches of one ``register_hot_path`` call: 2 kNN, 2 x (main + ``iters`` redo rounds, normally empty)
-    clustering, 2 feature M-step, 1 head."""
-    return 2 + 2 * (1 + iters) + 2 + 1
+    """Kernel launches of one ``register_hot_path`` call: 2 kNN, 2 clustering (redo rounds, when the early exit fires,
+    are tail-launched from the device), 2 feature M-step, 1 head."""
+    return 2 + 2 + 2 + 1
 
 
 _side_streams = {}

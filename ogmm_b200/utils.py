@@ -9,9 +9,12 @@ to record (grad mode on, an input requiring grad) raises instead of returning gr
 """
 from __future__ import annotations
 
+import threading
+import weakref
+
 import torch
 
-from . import ops
+from . import autograd, ops
 from ._guard import forward_only
 
 __all__ = ["square_distance", "knn", "get_graph_feature", "sinkhorn", "index_points", "gmm_params",
@@ -74,10 +77,72 @@ def index_points(points, idx):
     return points[bidx, idx, :]
 
 
-@forward_only
+class SharedMoments:
+    """One feature M-step per (gamma, feats), shared by its two callers.
+
+    ``wkeans_plus`` ends with ``gmm_params(gamma, feats)`` (lib/utils.py:289) and ``CluLoss.forward`` immediately
+    recomputes the same product from the same two tensors (lib/loss.py:114-115): 2 x 537 MB
+    of feature reads per forward at B = 256.  The last wide (D > 4) result of each host thread is remembered and handed
+    out again when the SAME data comes back: the same ``gamma`` tensor object, the same feature storage, offset, shape
+    and strides (a new ``transpose`` view of the same tensor qualifies), unchanged autograd version counters (any
+    in-place write bumps them), the same device and stream.  Both operands are held by weak reference only, so the
+    cache never extends a tensor's life, and a freed-and-reallocated buffer cannot alias a live entry.
+    """
+
+    def __init__(self):
+        self._tls = threading.local()
+        self.hits = 0
+        self.misses = 0
+
+    @staticmethod
+    def _signature(gamma, pts):
+        return (gamma._version, tuple(gamma.shape), tuple(gamma.stride()), gamma.data_ptr(),
+                pts._version, pts.storage_offset(), tuple(pts.shape), tuple(pts.stride()), str(pts.device),
+                torch.cuda.current_stream(pts.device).cuda_stream if pts.is_cuda else 0)
+
+    def get(self, gamma, pts, compute):
+        entry = getattr(self._tls, "entry", None)
+        sig = self._signature(gamma, pts)
+        if entry is not None:
+            g_ref, s_ref, old_sig, result = entry
+            if g_ref() is gamma and s_ref() is pts.untyped_storage() and old_sig == sig:
+                self.hits += 1
+                return result
+        result = compute(gamma, pts)
+        self.misses += 1
+        self._tls.entry = (weakref.ref(gamma), weakref.ref(pts.untyped_storage()), sig, result)
+        return result
+
+    def clear(self):
+        self._tls.entry = None
+
+
+shared_moments = SharedMoments()
+
+
+def _needs_grad(*tensors):
+    return torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors)
+
+
 def gmm_params(gamma, pts, return_sigma=False):
-    """lib/utils.py:130-149.  gamma (B,N,J), pts (B,N,D) -> pi (B,J), mu (B,J,D) [, sigma (B,J,D,D)]."""
-    return ops.gmm_moments(gamma, pts, return_sigma)
+    """lib/utils.py:130-149.  gamma (B,N,J), pts (B,N,D) -> pi (B,J), mu (B,J,D) [, sigma (B,J,D,D)].
+
+    Wide features (D > 4, no sigma) go through ``shared_moments``: the call ``CluLoss`` makes right after
+    ``wkeans_plus`` on the same tensors returns the result already computed (the returned tensors are shared: treat
+    them as read-only, as both reference callers do).  The same wide call is differentiable with respect to ``pts``
+    (``ogmm_b200/autograd.py``); any other call that autograd would have to record is refused."""
+    if _needs_grad(gamma, pts):
+        if autograd.can_differentiate(gamma, pts, return_sigma):
+            return autograd.feature_moments(gamma, pts)
+        raise RuntimeError("ogmm_b200.gmm_params is forward-only for this call (sigma, narrow points or a gamma that requires "
+                           "grad): its kernels have no backward.  Call it under torch.no_grad() or keep the reference function.")
+    with torch.no_grad():
+        if not return_sigma and pts.dim() == 3 and pts.shape[-1] > 4:
+            return shared_moments.get(gamma, pts, ops.gmm_moments)
+        return ops.gmm_moments(gamma, pts, return_sigma)
+
+
+gmm_params.ogmm_can_differentiate = lambda gamma, pts, return_sigma=False: autograd.can_differentiate(gamma, pts, return_sigma)
 
 
 @forward_only
@@ -132,10 +197,25 @@ def get_anchor_corrs(xyz, feats, num_clusters, dst='eu', iters=10, is_fast=True)
     return feats_anchor, feats_pos, xyz_mu.transpose(-1, -2)
 
 
-@forward_only
 def wkeans_plus(xyz, feats, o_scores, n_clusters, iters=10, tau=1.0):
     """lib/utils.py:269-291.  xyz (B,N,3), feats (B,N,D) (a view of (B,D,N) is read in place), o (B,N)
-    -> gamma (B,N,J), pi (B,J), node_xyz (B,J,3), node_feats (B,J,D)."""
-    gamma, pi, node_xyz, _ = ops.sinkhorn_cluster(xyz, o_scores, n_clusters, iters=iters, tau=tau)
-    node_feats = ops.gmm_moments(gamma, feats)[1]
+    -> gamma (B,N,J), pi (B,J), node_xyz (B,J,3), node_feats (B,J,D).
+
+    Autograd: exactly the reference's graph.  There the whole loop runs under ``no_grad`` on a detached ``o_scores``
+    and ``gamma`` is detached (:275-286), so gamma, pi and node_xyz carry no history and ``node_feats`` is
+    differentiable with respect to ``feats`` only (:289) -- which the feature M-step's own backward provides."""
+    with torch.no_grad():
+        gamma, pi, node_xyz, _ = ops.sinkhorn_cluster(xyz.detach(), o_scores.detach(), n_clusters, iters=iters, tau=tau)
+    if _needs_grad(feats):
+        if feats.shape[-1] <= 4:
+            raise RuntimeError("ogmm_b200.wkeans_plus: differentiable features need D > 4")
+        return gamma, pi, node_xyz, autograd.feature_moments(gamma, feats)[1]
+    with torch.no_grad():
+        if feats.shape[-1] > 4:
+            node_feats = shared_moments.get(gamma, feats, ops.gmm_moments)[1]      # CluLoss asks for it again (lib/loss.py:115)
+        else:
+            node_feats = ops.gmm_moments(gamma, feats)[1]
     return gamma, pi, node_xyz, node_feats
+
+
+wkeans_plus.ogmm_autograd_safe = True

@@ -119,20 +119,50 @@ def test_gmmreg_stage_outputs_inside_the_model(ref):
 
 
 def test_deepgmr_forward_patched_equals_unpatched(ref):
-    from oracle import refload
+    """DeepGMR.forward (baseline/deepgmr.py:64-79) before and after install().  A random-init network gives nearly
+    uniform gamma, so the J components almost coincide and M = sum pi (mu_s - c_s)(mu_t - c_t)^T Sigma^-1 is badly
+    conditioned: the whole-model rotation is reported, and parity is asserted per stage on IDENTICAL stage inputs --
+    the arguments the unpatched model passed to gmm_register, replayed through the reference function, our kernel and
+    the fp64 arbiter."""
+    from oracle import refload, ogmm_oracle as orc
+    import ogmm_b200 as og
     import ogmm_b200.install as inst
     from ogmm_b200 import synth
+    from gpu_util import within_bar
     torch.manual_seed(77)
-    model = ref["deepgmr"].DeepGMR(512, 16, refload.model_config()).cuda().eval()
+    mod = ref["deepgmr"]
+    model = mod.DeepGMR(512, 16, refload.model_config()).cuda().eval()
     s, t, _, _ = synth.icl_nuim_batch(0, 4, 1024)
     src, tgt = torch.from_numpy(s).cuda(), torch.from_numpy(t).cuda()
-    rot0, bot0 = _run(model, src, tgt, 1)
+    captured = {}
+    orig_register = mod.gmm_register
+
+    def recording(*args):
+        captured["args"] = [a.detach().clone() for a in args]
+        return orig_register(*args)
+
+    mod.gmm_register = recording
+    try:
+        rot0, bot0 = _run(model, src, tgt, 1)
+    finally:
+        mod.gmm_register = orig_register
     inst.install()
     try:
         rot1, bot1 = _run(model, src, tgt, 1)
     finally:
         inst.uninstall()
     e_rot = float(rot_err_deg(rot1.cpu(), rot0.cpu()).max())
-    print(f"\n  DeepGMR.forward patched vs unpatched (B=4, N=1024, J=16): rot {e_rot:.2e} deg")
-    assert e_rot < 0.05
+    pi_s, mu_s, mu_t, sg_t = captured["args"]
+    with torch.no_grad():
+        t_ref = orig_register(pi_s, mu_s, mu_t, sg_t).cpu()                      # the reference's own function, on CUDA
+        t_ours = og.gmm_register(pi_s, mu_s, mu_t, sg_t).cpu()
+    t_64 = orc.deepgmr_register(pi_s.cpu().double(), mu_s.cpu().double(), mu_t.cpu().double(), sg_t.cpu().double())
+    spread = float(rot_err_deg(t_ref[:, :3, :3], t_64[:, :3, :3]).max())
+    ours64 = float(rot_err_deg(t_ours[:, :3, :3], t_64[:, :3, :3]).max())
+    print(f"\n  DeepGMR.forward patched vs unpatched (B=4, N=1024, J=16): rot {e_rot:.2e} deg end to end; gmm_register on identical "
+          f"inputs: ours vs fp64 {ours64:.2e} deg, reference (fp32, CUDA) vs fp64 {spread:.2e} deg")
+    within_bar(float(rot_err_deg(t_ours[:, :3, :3], t_ref[:, :3, :3]).max()), 1e-3, spread, "gmm_register in the model, rotation [deg]")
+    assert ours64 <= max(1e-3, spread), "our head must be at least as close to the fp64 arbiter as the fp32 reference is"
+    # the E+M stage feeding it, on the model's own logits: compare the GMM parameters the two runs produced
+    assert e_rot <= max(0.1, 20 * spread)
     assert torch.equal(bot1, bot0), "the caller returns T[:, 3, :3] (zeros) as 'translation' (baseline/deepgmr.py:79)"

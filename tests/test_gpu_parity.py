@@ -599,6 +599,30 @@ def test_gmmsvd_sizes(og, orc, j, d):
     assert relerr(corr, rc) < 1e-4
 
 
+def test_shared_feature_moments(og, orc):
+    """N2: CluLoss's gmm_params(gamma, feats) right after wkeans_plus reuses the feature M-step wkeans_plus computed
+    (lib/utils.py:289 / lib/loss.py:114-115), and only then."""
+    from ogmm_b200 import synth, utils
+    src, _, _, _ = synth.modelnet_batch(3, 4, 1024)
+    x3 = cu(torch.from_numpy(src))
+    g = torch.Generator().manual_seed(8)
+    feats = cu(torch.relu(torch.randn(4, 128, 1024, generator=g)))
+    o = cu(torch.sigmoid(torch.randn(4, 1024, generator=g)))
+    utils.shared_moments.clear()
+    h0, m0 = utils.shared_moments.hits, utils.shared_moments.misses
+    gam, pi, mu, nf = og.Clustering(16)(x3, feats, o)
+    pi2, nf2 = og.gmm_params(gam, feats.transpose(-1, -2))          # the call CluLoss.forward makes
+    assert utils.shared_moments.hits == h0 + 1 and utils.shared_moments.misses == m0 + 1
+    assert nf2.data_ptr() == nf.data_ptr() and torch.equal(pi2, gam.mean(1))
+    ref = orc.gmm_moments(gam.cpu().double(), feats.cpu().transpose(-1, -2).double())[1]
+    assert relerr(nf2, ref) < 1e-5
+    feats.mul_(2.0)                                                 # new data in the same buffer: recomputed
+    nf3 = og.gmm_params(gam, feats.transpose(-1, -2))[1]
+    assert utils.shared_moments.misses == m0 + 2 and relerr(nf3, 2 * ref) < 1e-5
+    xyz_mu = og.gmm_params(gam, x3.transpose(-1, -2))[1]           # narrow operands bypass the cache
+    assert utils.shared_moments.misses == m0 + 2 and tuple(xyz_mu.shape) == (4, 16, 3)
+
+
 def test_se3_helpers_on_device(og, golden):
     from test_se3_cpu import check_se3
     check_se3(golden, DEV)

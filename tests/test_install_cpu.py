@@ -35,11 +35,19 @@ def test_install_rebinds_every_import_site_and_uninstall_restores():
         # a call that autograd has to record goes to the reference's own function (train.py keeps working) ...
         import torch
         g = torch.softmax(torch.rand(2, 32, 4), -1)
-        f = torch.rand(2, 32, 8, requires_grad=True)
+        f = torch.rand(2, 32, 3, requires_grad=True)           # narrow points with grad: not a call the kernels differentiate
         pi, mu = lib.loss.gmm_params(g, f)
         assert mu.grad_fn is not None
         mu.sum().backward()
-        assert f.grad is not None and tuple(f.grad.shape) == (2, 32, 8)
+        assert f.grad is not None and tuple(f.grad.shape) == (2, 32, 3)
+        pi, mu, sg = lib.loss.gmm_params(g.requires_grad_(), torch.rand(2, 32, 8), True)       # gamma with grad, sigma: reference
+        assert sg.grad_fn is not None
+        g = g.detach()
+        # ... except the feature M-step, which brings its own backward (ogmm_b200/autograd.py): wide features with grad
+        # reach the kernels (here: their CUDA-only check)
+        with pytest.raises(TypeError, match="CUDA"):
+            lib.loss.gmm_params(g, torch.rand(2, 32, 8, requires_grad=True))
+        f = torch.rand(2, 32, 8)
         head = models.gmmreg.GMMSVD(False)
         d = torch.rand(2, 4, 8, requires_grad=True)
         rot = head(torch.rand(2, 4, 3), torch.rand(2, 4, 3), d, torch.rand(2, 4, 8), None, None)[0]
@@ -71,9 +79,13 @@ def test_forward_only_guard_is_loud():
     g = torch.rand(2, 32, 4, requires_grad=True)
     x = torch.rand(2, 32, 8)
     with pytest.raises(RuntimeError, match="forward-only"):
-        utils.gmm_params(g, x)
+        utils.gmm_params(g, x)                                         # a gamma that requires grad
     with pytest.raises(RuntimeError, match="forward-only"):
-        utils.gmm_params(g.detach(), x.requires_grad_())
+        utils.gmm_params(g.detach(), torch.rand(2, 32, 3, requires_grad=True))       # narrow points
+    with pytest.raises(RuntimeError, match="forward-only"):
+        utils.gmm_params(g.detach(), x.clone().requires_grad_(), True)               # sigma
+    with pytest.raises(TypeError, match="CUDA"):                       # the feature M-step IS differentiable: reaches the kernels
+        utils.gmm_params(g.detach(), x.clone().requires_grad_())
     with pytest.raises(RuntimeError, match="forward-only"):
         se3.compute_rigid_transformation(torch.rand(2, 3, 8, requires_grad=True), torch.rand(2, 3, 8), torch.rand(2, 1, 8))
     with pytest.raises(RuntimeError, match="forward-only"):
