@@ -599,6 +599,49 @@ def test_gmmsvd_sizes(og, orc, j, d):
     assert relerr(corr, rc) < 1e-4
 
 
+@pytest.mark.parametrize("b,n,j,d,native", [(3, 1024, 16, 512, True), (2, 717, 16, 96, True), (2, 300, 24, 40, False), (1, 4096, 64, 128, True)])
+def test_feature_moments_backward(og, orc, b, n, j, d, native):
+    """N4 (start): d node_feats / d feats through the kernels' own backward against autograd of the fp64 oracle
+    (lib/utils.py:289 as train.py:57-75 differentiates it: gamma detached, gradient into feats only)."""
+    g = torch.Generator().manual_seed(b * n + d)
+    gamma = torch.softmax(torch.randn(b, n, j, generator=g) * 3, -1) * torch.rand(b, n, 1, generator=g)
+    base = torch.relu(torch.randn(b, d, n, generator=g)) if native else torch.relu(torch.randn(b, n, d, generator=g))
+    w = torch.randn(b, j, d, generator=g)
+    leaf = cu(base).requires_grad_()
+    view = leaf.transpose(-1, -2) if native else leaf
+    pi, mu = og.gmm_params(cu(gamma), view)
+    assert mu.requires_grad and not pi.requires_grad
+    (mu * cu(w)).sum().backward()
+    leaf64 = base.double().requires_grad_()
+    rpi, rmu = orc.gmm_moments(gamma.double(), leaf64.transpose(-1, -2) if native else leaf64)
+    (rmu * w.double()).sum().backward()
+    assert relerr(mu.detach(), rmu.detach()) < 1e-5
+    err = float((leaf.grad.cpu().double() - leaf64.grad).abs().max() / leaf64.grad.abs().max())
+    print(f"\n  feature M-step backward N={n} J={j} D={d} native={native}: grad rel err {err:.2e}")
+    assert err < 1e-5 and tuple(leaf.grad.shape) == tuple(base.shape)
+
+
+def test_wkeans_plus_differentiates_like_the_reference(og, orc):
+    """With a feature tensor that requires grad, wkeans_plus returns the reference's graph: gamma / pi / node_xyz without
+    history, node_feats differentiable into feats (lib/utils.py:275-289)."""
+    from ogmm_b200 import synth
+    src, _, _, _ = synth.modelnet_batch(2, 2, 1024)
+    xyz = torch.from_numpy(src).transpose(1, 2).contiguous()
+    g = torch.Generator().manual_seed(12)
+    feats = torch.relu(torch.randn(2, 64, 1024, generator=g))
+    o = torch.sigmoid(torch.randn(2, 1024, generator=g))
+    leaf = cu(feats).requires_grad_()
+    gam, pi, mu, nf = og.wkeans_plus(cu(xyz), leaf.transpose(-1, -2), cu(o).requires_grad_(), 16)
+    assert nf.requires_grad and not gam.requires_grad and not pi.requires_grad and not mu.requires_grad
+    nf.square().sum().backward()
+    leaf64 = feats.double().requires_grad_()
+    rg, rpi, rmu, rnf = orc.sinkhorn_kmeans(xyz.double(), leaf64.transpose(-1, -2), o.double(), 16)
+    rnf.square().sum().backward()
+    err = float((leaf.grad.cpu().double() - leaf64.grad).abs().max() / leaf64.grad.abs().max())
+    print(f"\n  wkeans_plus backward into feats: grad rel err {err:.2e} (includes the fp32-vs-fp64 difference of gamma)")
+    assert err < 1e-3
+
+
 def test_shared_feature_moments(og, orc):
     """N2: CluLoss's gmm_params(gamma, feats) right after wkeans_plus reuses the feature M-step wkeans_plus computed
     (lib/utils.py:289 / lib/loss.py:114-115), and only then."""
