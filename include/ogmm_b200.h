@@ -62,6 +62,15 @@ int ogmm_knn_graph(const float* src, int64_t s_sb, int64_t s_sn, int64_t s_sc,
                    int64_t B, int64_t N, int64_t M, int64_t C, int64_t k, int normalize,
                    int64_t* idx_out, float* dist_out, float* edge_out, ogmm_stream_t stream);
 
+/* Diagnostics of the 3-D selection kernel (knn_select.cu; C == 3, 256 <= M <= 4096, N <= 4096, k <= 24): same idx_out
+ * as ogmm_knn_graph plus counters in stats (device int32[16], caller-zeroed): [0] warps that redid their queries
+ * exhaustively, [1] warps, [2] sweep steps, [3] steps that merged, [4] / [5] sums of the per-warp largest collected /
+ * group counts, [6] [7] [8] warps with a column overflow / too many prefix ties / fewer than k groups. */
+int ogmm_knn3_select_stats(const float* src, int64_t s_sb, int64_t s_sn, int64_t s_sc,
+                           const float* dst, int64_t d_sb, int64_t d_sn, int64_t d_sc,
+                           int64_t B, int64_t N, int64_t M, int64_t k,
+                           int64_t* idx_out, int32_t* stats, ogmm_stream_t stream);
+
 /* square_distance alone (lib/utils.py:12-34): the dense matrix dist_out (B,N,M) contiguous, same arithmetic as the
  * selection kernels (dist_out of ogmm_knn_graph is a gather of it).  For callers outside the hot path (losses,
  * metrics); the hot path never materialises it. */

@@ -31,6 +31,7 @@ SIGNATURES = {
     "ogmm_last_error": (ctypes.c_char_p, []),
     "ogmm_device_info": (i32, [ctypes.POINTER(i32)] * 3),
     "ogmm_knn_graph": (i32, [c_f, i64, i64, i64, c_f, i64, i64, i64, i64, i64, i64, i64, i64, i32, c_i64p, c_f, c_f, vp]),
+    "ogmm_knn3_select_stats": (i32, [c_f, i64, i64, i64, c_f, i64, i64, i64, i64, i64, i64, i64, c_i64p, c_i32p, vp]),
     "ogmm_square_distance": (i32, [c_f, i64, i64, i64, c_f, i64, i64, i64, i64, i64, i64, i64, i32, c_f, vp]),
     "ogmm_knn_wide": (i32, [c_f, i64, i64, i64, c_f, i64, i64, i64, i64, i64, i64, i64, i64, i32, c_i64p, c_f, c_i32p, vp]),
     "ogmm_edge_gather": (i32, [c_f, i64, i64, i64, c_i64p, i64, i64, i64, i64, c_f, vp]),

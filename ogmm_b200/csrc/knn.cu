@@ -507,6 +507,18 @@ extern "C" __attribute__((visibility("default"))) int ogmm_knn_graph(const float
     return OGMM_OK;
 }
 
+// Diagnostic twin of the C == 3 route of ogmm_knn_graph: the selection kernel with its counters (see knn_select.cu).
+extern "C" __attribute__((visibility("default"))) int ogmm_knn3_select_stats(const float* src, int64_t s_sb, int64_t s_sn, int64_t s_sc,
+                                                                           const float* dst, int64_t d_sb, int64_t d_sn, int64_t d_sc,
+                                                                           int64_t B, int64_t N, int64_t M, int64_t k,
+                                                                           int64_t* idx_out, int32_t* stats, ogmm_stream_t stream) {
+    OGMM_REQUIRE(B >= 1 && N >= 1 && M >= 256 && M <= 4096 && N <= 4096 && k >= 1 && k <= 24 && k <= M && B < 65536, OGMM_EUNSUPPORTED,
+                 "ogmm_knn3_select_stats: outside the selection kernel's range");
+    OGMM_REQUIRE(src && dst && idx_out && stats, OGMM_EINVAL, "ogmm_knn3_select_stats: null pointer");
+    return ogmm_launch_knn3_select(src, s_sb, s_sn, s_sc, dst, d_sb, d_sn, d_sc, B, N, M, k, idx_out, nullptr, nullptr, stats,
+                                   as_stream(stream));
+}
+
 extern "C" __attribute__((visibility("default"))) int ogmm_edge_gather(const float* x, int64_t sb, int64_t sc, int64_t sn, const int64_t* idx,
                                 int64_t B, int64_t C, int64_t N, int64_t k, float* edge_out, ogmm_stream_t stream) {
     OGMM_REQUIRE(B >= 0 && C >= 1 && N >= 1 && k >= 1 && N < (1ll << 31) && C < (1ll << 20) && k < (1ll << 20),

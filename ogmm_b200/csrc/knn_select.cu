@@ -242,6 +242,7 @@ knn3_select_kernel(const float* __restrict__ src, int64_t s_sb, int64_t s_sn, in
 #pragma unroll
         for (int i = 0; i < kSelKeep; ++i) keep[i] = kSelBig;
         int gl = (pos >> 2) - 1, gr = pos >> 2;            // next group to visit on each side
+        int steps = 0, merges = 0;                         // diagnostics (stats != nullptr only)
         const unsigned rec_base = (unsigned)__cvta_generic_to_shared(s_rec);
         while (true) {
             const float bound = __uint_as_float(__float_as_uint(keep[K - 1]) | gmask);      // rounded up
@@ -252,6 +253,7 @@ knn3_select_kernel(const float* __restrict__ src, int64_t s_sb, int64_t s_sn, in
             go_l = __any_sync(kFull, go_l);
             go_r = __any_sync(kFull, go_r);
             if (!go_l && !go_r) break;
+            ++steps;
             float fresh[16];
             if (go_l) {
                 if (gl >= 7) {                             // whole block in range (warp-uniform): no per-group checks
@@ -287,6 +289,7 @@ knn3_select_kernel(const float* __restrict__ src, int64_t s_sb, int64_t s_sn, in
             if (!__any_sync(kFull, fmin16 < keep[kSelVisit])) continue;
             bitonic_sort_regs<16>(fresh);
             merge_keys(keep, fresh);
+            ++merges;
         }
 
         // ================= pass 2: collect from the groups the first k (+ ties) keys name =================
@@ -313,6 +316,15 @@ knn3_select_kernel(const float* __restrict__ src, int64_t s_sb, int64_t s_sn, in
                         ++cnt;
                     }
                 }
+            }
+        }
+        if (stats) {
+            const int mx = __reduce_max_sync(kFull, valid ? cnt : 0), ng = __reduce_max_sync(kFull, valid ? n_g : 0);
+            const unsigned over = __ballot_sync(kFull, valid && cnt > kSelCap), ties = __ballot_sync(kFull, valid && n_g > kSelVisit);
+            const unsigned few = __ballot_sync(kFull, valid && !(keep[K - 1] < 0.5f * kSelBig));
+            if (lane == 0) {
+                atomicAdd(stats + 1, 1); atomicAdd(stats + 2, steps); atomicAdd(stats + 3, merges); atomicAdd(stats + 4, mx);
+                atomicAdd(stats + 5, ng); atomicAdd(stats + 6, over != 0); atomicAdd(stats + 7, ties != 0); atomicAdd(stats + 8, few != 0);
             }
         }
         redo = redo || (valid && cnt > kSelCap);
@@ -382,7 +394,9 @@ knn3_select_kernel(const float* __restrict__ src, int64_t s_sb, int64_t s_sn, in
 using namespace ogmm;
 
 // Called by ogmm_knn_graph for C == 3, normalize == 0, 256 <= M <= 4096, N <= 4096, k <= 24.
-// `stats` (optional, device int32, caller-zeroed): number of warps that took the exhaustive redo path.
+// `stats` (optional, device int32[16], caller-zeroed): [0] warps that took the exhaustive redo path, [1] warps, [2] sweep
+// steps, [3] steps that merged, [4] sum over warps of the largest collected count, [5] of the largest group count,
+// [6] / [7] / [8] warps with a column overflow / too many prefix ties / fewer than k groups.
 int ogmm_launch_knn3_select(const float* src, int64_t s_sb, int64_t s_sn, int64_t s_sc,
                             const float* dst, int64_t d_sb, int64_t d_sn, int64_t d_sc,
                             int64_t B, int64_t N, int64_t M, int64_t k,

@@ -937,11 +937,11 @@ static inline int launch_sinkhorn(SinkhornParams P, void* workspace, int64_t wor
             if (P.N <= 256) return launch_sinkhorn_variant<256, 1, true, true>(P, s);
             if (P.N <= 512) return launch_sinkhorn_variant<256, 2, true, true>(P, s);
             if (P.J == 16) {
-                // 4 warps x 8 points per thread: the per-warp overheads of an iteration (column butterfly, partial-sum
-                // fold, change tracking) are paid by half as many warps per cloud; OGMM_CLUSTER_NT=256 keeps 8 warps x 4
+                // OGMM_CLUSTER_NT=128 selects 4 warps x 8 points per thread (half the per-warp overheads per cloud, but 255
+                // registers and 8 warps per SM): measured slower on B200, 0.534 vs 0.462 ms per 2 x 256 clouds
                 const char* nt = getenv("OGMM_CLUSTER_NT");
-                if (nt && nt[0] == '2') return launch_sinkhorn_variant<256, 4, true, true, true>(P, s);
-                return launch_sinkhorn_variant<128, 8, true, true, true>(P, s);
+                if (nt && nt[0] == '1') return launch_sinkhorn_variant<128, 8, true, true, true>(P, s);
+                return launch_sinkhorn_variant<256, 4, true, true, true>(P, s);
             }
             return launch_sinkhorn_variant<256, 4, true, true>(P, s);
         }

@@ -112,17 +112,23 @@ def test_knn_nan_and_inf_inputs_stay_in_range(og):
     bad = x.clone()
     bad[0, 5] = float("nan")
     bad[1, 7, 1] = float("inf")
-    idx, _, edge = og.ops.knn_graph(cu(bad), cu(bad), 20, want_edge=True)
+    bad_d = cu(bad)
+    idx, _, edge = og.ops.knn_graph(bad_d, bad_d, 20, want_edge=True)
     torch.cuda.synchronize()
     assert int(idx.min()) >= 0 and int(idx.max()) < 600
-    allnan = torch.full((1, 64, 3), float("nan"))
-    idx2, _, _ = og.ops.knn_graph(cu(allnan), cu(allnan), 8, want_edge=True)
+    allnan = cu(torch.full((1, 64, 3), float("nan")))
+    idx2, _, _ = og.ops.knn_graph(allnan, allnan, 8, want_edge=True)
+    big_nan = cu(torch.full((1, 600, 3), float("nan")))
+    idx4 = og.ops.knn_graph(big_nan, big_nan, 20, want_edge=True)[0]
+    torch.cuda.synchronize()
+    assert int(idx4.min()) >= 0 and int(idx4.max()) < 600
     torch.cuda.synchronize()
     assert int(idx2.min()) >= 0 and int(idx2.max()) < 64
     for n, c in ((300, 3), (300, 16), (5000, 3)):                   # exhaustive / generic kernels
         y = torch.rand(1, n, c, generator=g)
         y[0, 1] = float("nan")
-        i3 = og.ops.knn_graph(cu(y), cu(y), 8, normalize=(c == 16))[0]
+        y = cu(y)
+        i3 = og.ops.knn_graph(y, y, 8, normalize=(c == 16))[0]
         assert int(i3.min()) >= 0 and int(i3.max()) < n
     del clean
 
@@ -656,7 +662,7 @@ def test_shared_feature_moments(og, orc):
     gam, pi, mu, nf = og.Clustering(16)(x3, feats, o)
     pi2, nf2 = og.gmm_params(gam, feats.transpose(-1, -2))          # the call CluLoss.forward makes
     assert utils.shared_moments.hits == h0 + 1 and utils.shared_moments.misses == m0 + 1
-    assert nf2.data_ptr() == nf.data_ptr() and torch.equal(pi2, gam.mean(1))
+    assert nf2.data_ptr() == nf.data_ptr() and torch.allclose(pi2, gam.mean(1), rtol=1e-5, atol=1e-8)
     ref = orc.gmm_moments(gam.cpu().double(), feats.cpu().transpose(-1, -2).double())[1]
     assert relerr(nf2, ref) < 1e-5
     feats.mul_(2.0)                                                 # new data in the same buffer: recomputed

@@ -11,9 +11,11 @@ from ogmm_b200 import se3, utils
 
 def check_se3(golden, dev="cpu"):
     g = {k: v.to(dev) for k, v in golden("se3").items()}
-    assert torch.equal(se3.torch_inverse(g["g1"]), g["inv"])
-    assert torch.equal(se3.torch_concatenate(g["g1"], g["g2"]), g["cat"])
-    assert torch.equal(se3.torch_transform(g["g1"], g["cloud"]), g["moved"])
+    # bit-exact on the CPU (same ATen ops as the reference ran); a few ulp on the GPU, whose matmul sums in another order
+    same = torch.equal if str(dev) == "cpu" else (lambda a, b: torch.allclose(a, b, rtol=1e-6, atol=1e-6))
+    assert same(se3.torch_inverse(g["g1"]), g["inv"])
+    assert same(se3.torch_concatenate(g["g1"], g["g2"]), g["cat"])
+    assert same(se3.torch_transform(g["g1"], g["cloud"]), g["moved"])
     rot, t = se3.decompose_trans(g["integ"])
     assert tuple(rot.shape) == (2, 3, 3) and tuple(t.shape) == (2, 3, 1)
     assert torch.equal(rot, g["g1"][:, :, :3]) and torch.equal(t, g["g1"][:, :, 3:4])
@@ -26,7 +28,7 @@ def check_se3(golden, dev="cpu"):
     ident = se3.torch_concatenate(g["g1"], se3.torch_inverse(g["g1"]))
     assert torch.allclose(ident, se3.torch_identity(2).to(dev), atol=1e-6)
     moved, normals = se3.torch_transform(g["g1"], g["cloud"], g["cloud"])
-    assert torch.equal(moved, g["moved"]) and torch.allclose(normals, g["moved"] - g["g1"][:, None, :, 3], atol=1e-5)
+    assert same(moved, g["moved"]) and torch.allclose(normals, g["moved"] - g["g1"][:, None, :, 3], atol=1e-5)
     f = {k: v.to(dev) for k, v in golden("fps").items()}
     assert torch.equal(utils.index_points(f["xyz"], f["ids_center"]), f["gathered"])
 

@@ -33,10 +33,22 @@ def with_env(name, fn):
         del os.environ[name]
 
 
-def redo_count(src, dst, k):
-    """warps that took the exhaustive redo path (direct call of the launcher's diagnostic counter is not exported: the
-    count is inferred from a stats-enabled debug build only); placeholder returning None."""
-    return None
+def select_stats(src, dst, k):
+    """Counters of the selection kernel (ogmm_knn3_select_stats), or None outside its range."""
+    B, N, _ = src.shape
+    M = dst.shape[1]
+    if not (256 <= M <= 4096 and N <= 4096 and k <= 24):
+        return None
+    idx = torch.empty((B, N, k), dtype=torch.int64, device=src.device)
+    st = torch.zeros(16, dtype=torch.int32, device=src.device)
+    rc = _lib.load().ogmm_knn3_select_stats(src.data_ptr(), *src.stride(), dst.data_ptr(), *dst.stride(), B, N, M, k,
+                                            idx.data_ptr(), st.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "ogmm_knn3_select_stats")
+    v = st.cpu().tolist()
+    w = max(v[1], 1)
+    return {"warps": v[1], "redo_frac": v[0] / w, "steps_per_warp": v[2] / w, "merges_per_warp": v[3] / w,
+            "max_collected_per_warp": v[4] / w, "max_groups_per_warp": v[5] / w, "overflow_frac": v[6] / w,
+            "tie_frac": v[7] / w, "few_groups_frac": v[8] / w}
 
 
 def case(name, src, dst, k, edge, reps=20):
@@ -50,7 +62,7 @@ def case(name, src, dst, k, edge, reps=20):
     t_old = with_env("OGMM_KNN_SWEEP_INSERT", lambda: timed(run, reps))
     row = {"case": name, "B": src.shape[0], "N": src.shape[1], "M": dst.shape[1], "k": k, "edge": edge,
            "identical_to_sweep_insert": same_old, "identical_to_exhaustive": same_exh,
-           "select_ms": t_new, "sweep_insert_ms": t_old, "speedup": t_old / t_new}
+           "select_ms": t_new, "sweep_insert_ms": t_old, "speedup": t_old / t_new, "stats": select_stats(src, dst, k)}
     print(json.dumps(row), flush=True)
     return row
 
