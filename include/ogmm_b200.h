@@ -64,8 +64,8 @@ int ogmm_knn_graph(const float* src, int64_t s_sb, int64_t s_sn, int64_t s_sc,
 
 /* Diagnostics of the 3-D selection kernel (knn_select.cu; C == 3, 256 <= M <= 4096, N <= 4096, k <= 24): same idx_out
  * as ogmm_knn_graph plus counters in stats (device int32[16], caller-zeroed): [0] warps that redid their queries
- * exhaustively, [1] warps, [2] sweep steps, [3] steps that merged, [4] / [5] sums of the per-warp largest collected /
- * group counts, [6] [7] [8] warps with a column overflow / too many prefix ties / fewer than k groups. */
+ * exhaustively, [1] warps, [2] sweep steps, [3] steps that merged, [4] insert rounds, [5] sum of the per-warp largest
+ * group counts, [7] [8] warps with too many prefix ties / fewer than k groups. */
 int ogmm_knn3_select_stats(const float* src, int64_t s_sb, int64_t s_sn, int64_t s_sc,
                            const float* dst, int64_t d_sb, int64_t d_sn, int64_t d_sc,
                            int64_t B, int64_t N, int64_t M, int64_t k,
@@ -95,6 +95,20 @@ int ogmm_knn_wide(const float* src, int64_t s_sb, int64_t s_sn, int64_t s_sc,
  *   (NOT batch-offset; unlike the reference :57 the index tensor is not modified). */
 int ogmm_edge_gather(const float* x, int64_t sb, int64_t sc, int64_t sn, const int64_t* idx,
                      int64_t B, int64_t C, int64_t N, int64_t k, float* edge_out, ogmm_stream_t stream);
+
+/* ---- N3: edge gather fused into the first EdgeConv layer -----------------------------------------
+ * Replaces, for inference, models/dgcnn.py:137-141: get_graph_feature (lib/utils.py:47-66) -> conv1 (1x1 Conv2d
+ * 6 -> C, no bias) -> bn1 (eval) -> ReLU -> max over k, without materialising the (B,6,N,k) edge tensor.
+ *   x (B,3,N) strided view (strides b, c, n); idx (B,N,k) int64 contiguous, values in [0,N);
+ *   weight (C,6) contiguous (conv1.weight viewed as (C,6)); scale, shift (C): BatchNorm folded by the caller,
+ *   scale = gamma / sqrt(running_var + eps), shift = beta - running_mean * scale.
+ *   act_out (optional) (B,C,N,k) contiguous = relu(bn1(conv1(edge))), the tensor conv2 consumes;
+ *   max_out (B,C,N) contiguous = its maximum over k (the reference's x1 is max_out viewed as (B,C,N,1)).
+ *   k <= 32; the cloud (12 N bytes) must fit shared memory. */
+int ogmm_edge_conv_max(const float* x, int64_t x_sb, int64_t x_sc, int64_t x_sn, const int64_t* idx,
+                       const float* weight, const float* scale, const float* shift,
+                       int64_t B, int64_t N, int64_t k, int64_t C,
+                       float* act_out, float* max_out, ogmm_stream_t stream);
 
 /* ---- farthest point sampling -----------------------------------------------------------------
  * Replaces lib/utils.py:170-198 farthest_point_sample.  xyz (B,N,3) strided view.

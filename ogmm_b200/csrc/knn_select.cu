@@ -12,23 +12,24 @@
 //           32 smallest keys seen so far.  Its k-th entry is an upper bound of the true k-th distance (k different
 //           groups each hold a candidate at or below it) and prunes the sweep.
 //   pass 2  revisits ONLY the groups named by the first k (+ ties) keys -- about 80 candidates per query instead of the
-//           ~450 of the slab, each lane walking its own groups -- and appends the candidates at or below the bound
-//           (k + a few) to a shared-memory column.
-//   final   those few candidates are inserted into the sorted 64-bit (distance, index) list; every lane has work in
-//           every round, so ~25 rounds replace ~190.
+//           ~450 of the slab, each lane walking its own groups -- eight groups at a time: the candidates at or below
+//           the bound (at most 32 per chunk, so the shared-memory column cannot overflow) are appended to the column
+//           and then inserted into the sorted 64-bit (distance, index) list; every lane has work in every round, so
+//           ~30 rounds replace ~190.  Once the list is full its exact k-th distance tightens the bound for the
+//           remaining chunks (the keys are in ascending order of group minimum, so the early chunks hold the winners).
 //
 // Exactness.  Let T be the key prefix (all bits above the group id) of the k-th smallest group key.  Any true
 // neighbour c lies in a group whose minimum is <= d(c) <= (k-th distance); if that group's prefix exceeded T, the k
 // group minima of the first k keys would all be strictly smaller than d(c), contradicting c being among the k smallest.
 // So every true neighbour sits in a group whose key prefix is <= T: the first k keys plus any later keys with prefix
 // == T (the list keeps 32, so up to 12 such ties are visible).  The bound used for pruning and collecting is the k-th
-// key with its id bits set to one, i.e. rounded UP.  Warps that meet more prefix ties than fit, fewer than k groups, or
-// more collected candidates than the column holds redo their 32 queries exhaustively (exact, slow, rare).
+// key with its id bits set to one, i.e. rounded UP.  Warps that meet more prefix ties than fit (clouds of coincident
+// points) or fewer than k groups redo their 32 queries exhaustively (exact, slow, rare).
 #include "knn_common.cuh"
 
 namespace ogmm {
 
-constexpr int kSelCap = 48;                 // collected candidates per query held in shared memory
+constexpr int kSelCap = 32;                 // collected candidates per query and chunk (8 groups x 4) held in shared memory
 constexpr int kSelKeep = 32;                // group keys kept per query (registers)
 constexpr int kSelVisit = 24;               // groups revisited at most: k + prefix ties
 constexpr float kSelBig = 1.0e38f;          // finite sentinel: stays finite with id bits OR-ed in
@@ -299,50 +300,56 @@ knn3_select_kernel(const float* __restrict__ src, int64_t s_sb, int64_t s_sn, in
 #pragma unroll
         for (int j = K; j < kSelKeep; ++j) n_g += ((__float_as_uint(keep[j]) & ~gmask) == (kth & ~gmask)) ? 1 : 0;   // sorted: ties are contiguous
         bool redo = valid && (n_g > kSelVisit || !(keep[K - 1] < 0.5f * kSelBig));
-        int cnt = 0;
-#pragma unroll
-        for (int j = 0; j < kSelVisit; ++j) {
-            if (j < n_g) {
-                const int g = (int)(__float_as_uint(keep[j]) & gmask);
-                float v[4];
-                group_distances(rec_base + 64u * (unsigned)g, Q, v);
-#pragma unroll
-                for (int m = 0; m < 4; ++m) {
-                    if (v[m] <= tau) {
-                        if (cnt < kSelCap) {
-                            s_buf_d[cnt * kSwThreads + tid] = fmaxf(v[m], 1e-12f);
-                            s_buf_p[cnt * kSwThreads + tid] = (unsigned short)(4 * g + m);
-                        }
-                        ++cnt;
-                    }
-                }
-            }
-        }
+        redo = __any_sync(kFull, redo);
         if (stats) {
-            const int mx = __reduce_max_sync(kFull, valid ? cnt : 0), ng = __reduce_max_sync(kFull, valid ? n_g : 0);
-            const unsigned over = __ballot_sync(kFull, valid && cnt > kSelCap), ties = __ballot_sync(kFull, valid && n_g > kSelVisit);
+            const int ng = __reduce_max_sync(kFull, valid ? n_g : 0);
+            const unsigned ties = __ballot_sync(kFull, valid && n_g > kSelVisit);
             const unsigned few = __ballot_sync(kFull, valid && !(keep[K - 1] < 0.5f * kSelBig));
             if (lane == 0) {
-                atomicAdd(stats + 1, 1); atomicAdd(stats + 2, steps); atomicAdd(stats + 3, merges); atomicAdd(stats + 4, mx);
-                atomicAdd(stats + 5, ng); atomicAdd(stats + 6, over != 0); atomicAdd(stats + 7, ties != 0); atomicAdd(stats + 8, few != 0);
+                atomicAdd(stats + 1, 1); atomicAdd(stats + 2, steps); atomicAdd(stats + 3, merges);
+                atomicAdd(stats + 5, ng); atomicAdd(stats + 7, ties != 0); atomicAdd(stats + 8, few != 0);
             }
         }
-        redo = redo || (valid && cnt > kSelCap);
-        redo = __any_sync(kFull, redo);
 
-        // ================= final: exact (distance, index) order of the few collected candidates =================
         TopK64<K> top;
         top.init(nullptr, nullptr, tid, valid);
         if (!redo) {
-            const int most = __reduce_max_sync(kFull, valid ? cnt : 0);
-            for (int s = 0; s < most; ++s) {
-                u64 kv = kEmptyKey;
-                if (valid && s < cnt) {
-                    const unsigned p = s_buf_p[s * kSwThreads + tid];
-                    kv = ((u64)__float_as_uint(s_buf_d[s * kSwThreads + tid]) << 32) | ((unsigned)s_cord[p] << 16) | p;
+            float bound2 = tau;                            // collect bound; the exact k-th distance once the list is full
+            int rounds = 0;
+#pragma unroll
+            for (int c0 = 0; c0 < kSelVisit; c0 += 8) {
+                if (!__any_sync(kFull, valid && c0 < n_g)) break;
+                int cnt = 0;
+#pragma unroll
+                for (int j = c0; j < c0 + 8; ++j) {
+                    if (j < n_g) {
+                        const int g = (int)(__float_as_uint(keep[j]) & gmask);
+                        float v[4];
+                        group_distances(rec_base + 64u * (unsigned)g, Q, v);
+#pragma unroll
+                        for (int m = 0; m < 4; ++m) {
+                            if (v[m] <= bound2) {          // at most 32 per chunk: the column cannot overflow
+                                s_buf_d[cnt * kSwThreads + tid] = fmaxf(v[m], 1e-12f);
+                                s_buf_p[cnt * kSwThreads + tid] = (unsigned short)(4 * g + m);
+                                ++cnt;
+                            }
+                        }
+                    }
                 }
-                if (__any_sync(kFull, kv < top.key[K - 1])) top.insert(kv);
+                // exact (distance, index) order: every lane's s-th collected candidate goes in together
+                const int most = __reduce_max_sync(kFull, valid ? cnt : 0);
+                rounds += most;
+                for (int s2 = 0; s2 < most; ++s2) {
+                    u64 kv = kEmptyKey;
+                    if (valid && s2 < cnt) {
+                        const unsigned p = s_buf_p[s2 * kSwThreads + tid];
+                        kv = ((u64)__float_as_uint(s_buf_d[s2 * kSwThreads + tid]) << 32) | ((unsigned)s_cord[p] << 16) | p;
+                    }
+                    if (__any_sync(kFull, kv < top.key[K - 1])) top.insert(kv);
+                }
+                bound2 = fminf(bound2, __uint_as_float((unsigned)(top.key[K - 1] >> 32)));      // +inf bits until the list is full
             }
+            if (stats && lane == 0) atomicAdd(stats + 4, rounds);
         } else {
             // exhaustive redo of this warp's queries: every group, straight into the sorted list (exact by construction)
             if (lane == 0 && stats) atomicAdd(stats, 1);
@@ -366,6 +373,11 @@ knn3_select_kernel(const float* __restrict__ src, int64_t s_sb, int64_t s_sn, in
             float* dout = dist_out ? dist_out + ((int64_t)b * N + q) * k : nullptr;
             float* eo = edge_out ? edge_out + ((int64_t)b * N + q) * (int64_t)k * 6 : nullptr;
             const float* recf = reinterpret_cast<const float*>(s_rec);
+            // rows of k int64 / 6k floats: 16-byte stores when k is even (row pitches 8k and 24k bytes are then 16-byte multiples)
+            const bool vec = ((k & 1) == 0) && ((reinterpret_cast<uintptr_t>(idx_out) & 15) == 0) &&
+                             (edge_out == nullptr || (reinterpret_cast<uintptr_t>(edge_out) & 15) == 0);
+            float e6[12];
+            long long nb2[2];
 #pragma unroll
             for (int j = 0; j < K; ++j) {
                 if (j < k) {
@@ -373,14 +385,31 @@ knn3_select_kernel(const float* __restrict__ src, int64_t s_sb, int64_t s_sn, in
                     // an unfilled slot (non-finite coordinates: no distance ever compares) stays in range
                     const unsigned p = min(low & 0xffffu, (unsigned)(M - 1));
                     const int nb = top.key[j] == kEmptyKey ? min(j, M - 1) : (int)(low >> 16);
-                    io[j] = nb;
                     if (dout) dout[j] = __uint_as_float((unsigned)(top.key[j] >> 32));
+                    const int h = j & 1;
+                    nb2[h] = nb;
                     if (eo) {
                         // self graph: the neighbour's coordinates are in the staged records (-2 x is exact, so is -0.5 * it)
                         const float* rc = recf + 16 * (p >> 2) + 8 * ((p & 3) >> 1) + (p & 1);
-                        const float nx = -0.5f * rc[0], ny = -0.5f * rc[2], nz = -0.5f * rc[4];
-                        eo[6 * j + 0] = nx - qx; eo[6 * j + 1] = ny - qy; eo[6 * j + 2] = nz - qz;
-                        eo[6 * j + 3] = qx; eo[6 * j + 4] = qy; eo[6 * j + 5] = qz;
+                        e6[6 * h + 0] = -0.5f * rc[0] - qx; e6[6 * h + 1] = -0.5f * rc[2] - qy; e6[6 * h + 2] = -0.5f * rc[4] - qz;
+                        e6[6 * h + 3] = qx; e6[6 * h + 4] = qy; e6[6 * h + 5] = qz;
+                    }
+                    if (vec) {
+                        if (h == 1) {
+                            *reinterpret_cast<longlong2*>(io + j - 1) = make_longlong2(nb2[0], nb2[1]);
+                            if (eo) {
+                                float4* o4 = reinterpret_cast<float4*>(eo + 6 * (j - 1));
+                                o4[0] = make_float4(e6[0], e6[1], e6[2], e6[3]);
+                                o4[1] = make_float4(e6[4], e6[5], e6[6], e6[7]);
+                                o4[2] = make_float4(e6[8], e6[9], e6[10], e6[11]);
+                            }
+                        }
+                    } else {
+                        io[j] = nb;
+                        if (eo) {
+#pragma unroll
+                            for (int c = 0; c < 6; ++c) eo[6 * j + c] = e6[6 * h + c];
+                        }
                     }
                 }
             }
@@ -395,8 +424,8 @@ using namespace ogmm;
 
 // Called by ogmm_knn_graph for C == 3, normalize == 0, 256 <= M <= 4096, N <= 4096, k <= 24.
 // `stats` (optional, device int32[16], caller-zeroed): [0] warps that took the exhaustive redo path, [1] warps, [2] sweep
-// steps, [3] steps that merged, [4] sum over warps of the largest collected count, [5] of the largest group count,
-// [6] / [7] / [8] warps with a column overflow / too many prefix ties / fewer than k groups.
+// steps, [3] steps that merged, [4] insert rounds, [5] sum over warps of the largest group count, [7] / [8] warps with
+// too many prefix ties / fewer than k groups.
 int ogmm_launch_knn3_select(const float* src, int64_t s_sb, int64_t s_sn, int64_t s_sc,
                             const float* dst, int64_t d_sb, int64_t d_sn, int64_t d_sc,
                             int64_t B, int64_t N, int64_t M, int64_t k,

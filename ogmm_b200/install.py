@@ -53,6 +53,7 @@ PATCH_TABLE = {
 
 _saved = {}
 _reclassed = []
+_saved_methods = {}
 
 
 def _needs_grad(args, kwargs):
@@ -114,6 +115,20 @@ def install(modules=None, model=None):
             new = _class_dispatcher(repl, orig) if isinstance(repl, type) else _dispatcher(repl, orig)
             setattr(mod, attr, new)
             done.append(f"{mod_name}.{attr}")
+    # DGCNN.forward: the kNN graph and the fused edge gather + conv1 + bn1 + ReLU + max (N3) when the module runs in
+    # eval mode without autograd; the reference's own forward (with the patched knn / get_graph_feature) otherwise
+    dg = sys.modules.get("models.dgcnn")
+    if dg is not None and (modules is None or "models.dgcnn" in modules) and hasattr(dg, "DGCNN"):
+        cls = dg.DGCNN
+        orig_forward = _saved_methods.setdefault((cls, "forward"), cls.forward)
+
+        def forward(self, x, _orig=orig_forward):
+            if self.training or _needs_grad((x,), {}) or (torch.is_grad_enabled() and any(p.requires_grad for p in self.conv1.parameters())):
+                return _orig(self, x)
+            return _modules.dgcnn_forward(self, x)
+
+        cls.forward = forward
+        done.append("models.dgcnn.DGCNN.forward")
     if model is not None:
         for m in model.modules():
             for (mod_name, attr), orig in _saved.items():
@@ -126,6 +141,9 @@ def install(modules=None, model=None):
 
 
 def uninstall():
+    for (cls, name), orig in list(_saved_methods.items()):
+        setattr(cls, name, orig)
+        del _saved_methods[(cls, name)]
     for m, orig in _reclassed:
         m.__class__ = orig
     _reclassed.clear()

@@ -16,7 +16,7 @@ from ._guard import forward_only
 from .se3 import compute_rigid_transformation
 from .utils import wkeans_plus
 
-__all__ = ["Clustering", "GMMSVD", "graph_features", "gmm_register", "deepgmr_em"]
+__all__ = ["Clustering", "GMMSVD", "graph_features", "gmm_register", "deepgmr_em", "edge_conv1", "dgcnn_forward"]
 
 
 class Clustering(nn.Module):
@@ -72,3 +72,39 @@ def gmm_register(pi_s, mu_s, mu_t, sigma_t):
 def deepgmr_em(logits, pts):
     """baseline/deepgmr.py:71-74 fused: logits (B,J,N), pts (B,3,N) -> gamma (B,J,N), pi, mu, sigma."""
     return ops.softmax_moments(logits, pts)
+
+
+def _fold_bn(bn):
+    """BatchNorm in eval mode as y * scale + shift."""
+    scale = bn.weight / torch.sqrt(bn.running_var + bn.eps) if bn.affine else 1.0 / torch.sqrt(bn.running_var + bn.eps)
+    shift = (bn.bias if bn.affine else 0.0) - bn.running_mean * scale
+    return scale.float(), shift.float()
+
+
+@forward_only
+def edge_conv1(x, idx, conv, bn, want_act=True):
+    """models/dgcnn.py:137-141 in one launch, for inference: x (B,3,N), idx (B,N,k), conv = Conv2d(6, C, 1, bias=False),
+    bn = BatchNorm2d(C) in eval mode -> (relu(bn(conv(edge))) (B,C,N,k) | None, its max over k (B,C,N,1))."""
+    if bn.training:
+        raise RuntimeError("edge_conv1 folds BatchNorm's running statistics: the module must be in eval() mode")
+    scale, shift = _fold_bn(bn)
+    act, pooled = ops.edge_conv_max(x, idx, conv.weight.reshape(conv.out_channels, -1), scale, shift, want_act)
+    return act, pooled.unsqueeze(-1)
+
+
+def dgcnn_forward(self, x):
+    """Drop-in body for ``DGCNN.forward`` (models/dgcnn.py:133-154) in eval / no_grad mode: kNN graph (K1), then the edge
+    gather fused with conv1 + bn1 + ReLU + max (N3); conv2..conv5 are the module's own PyTorch layers, unchanged."""
+    import torch.nn.functional as F
+    batch_size, _, num_points = x.size()
+    pts = x.transpose(-1, -2)
+    idx = ops.knn_graph(pts, pts, self.k)[0]
+    x, x1 = edge_conv1(x, idx, self.conv1, self.bn1)
+    x = F.relu(self.bn2(self.conv2(x)))
+    x2 = x.max(dim=-1, keepdim=True)[0]
+    x = F.relu(self.bn3(self.conv3(x)))
+    x3 = x.max(dim=-1, keepdim=True)[0]
+    x = F.relu(self.bn4(self.conv4(x)))
+    x4 = x.max(dim=-1, keepdim=True)[0]
+    x = torch.cat((x1, x2, x3, x4), dim=1)
+    return F.relu(self.bn5(self.conv5(x))).view(batch_size, -1, num_points)

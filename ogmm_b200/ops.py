@@ -95,6 +95,26 @@ def edge_gather(x, idx):
     return edge
 
 
+def edge_conv_max(x, idx, weight, scale, shift, want_act=True):
+    """x (B,3,N) view, idx (B,N,k) int64, weight (C,6), scale / shift (C) -> act (B,C,N,k) | None, pooled (B,C,N)."""
+    _need_cuda_f32("x", x); _need_cuda_f32("weight", weight); _need_cuda_f32("scale", scale); _need_cuda_f32("shift", shift)
+    if idx.dtype != torch.int64 or not idx.is_cuda:
+        raise TypeError("edge_conv_max: idx must be a CUDA int64 tensor")
+    B, three, N = x.shape
+    k = idx.shape[-1]
+    C = weight.shape[0]
+    if three != 3 or tuple(idx.shape) != (B, N, k) or weight.numel() != C * 6 or scale.numel() != C or shift.numel() != C:
+        raise ValueError("edge_conv_max: expected x (B,3,N), idx (B,N,k), weight (C,6), scale (C), shift (C)")
+    idx, weight, scale, shift = idx.contiguous(), weight.reshape(C, 6).contiguous(), scale.contiguous(), shift.contiguous()
+    act = torch.empty((B, C, N, k), dtype=torch.float32, device=x.device) if want_act else None
+    pooled = torch.empty((B, C, N), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        st = _lib.load().ogmm_edge_conv_max(x.data_ptr(), *x.stride(), idx.data_ptr(), weight.data_ptr(), scale.data_ptr(),
+                                            shift.data_ptr(), B, N, k, C, _ptr(act), pooled.data_ptr(), _stream(x))
+    _lib.check(st, "ogmm_edge_conv_max")
+    return act, pooled
+
+
 def fps(xyz, npoint, start=None, want_points=False):
     """xyz (B,N,3) view -> ids (B,npoint) int64 [, points (B,npoint,3)].  start=None: is_center."""
     _need_cuda_f32("xyz", xyz)

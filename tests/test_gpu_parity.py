@@ -251,6 +251,40 @@ def test_edge_features(og, orc, golden):
     assert torch.equal(fused.cpu(), orc.edge_features(x, 20, idx.cpu()))
 
 
+def test_edge_conv1_fused(og):
+    """N3 (models/dgcnn.py:137-141): edge gather + conv1 + bn1(eval) + ReLU + max over k in one kernel against the same
+    layers in PyTorch fed with the materialised edge tensor; 1e-5 relative as the task states it."""
+    from ogmm_b200 import modules
+    g = torch.Generator().manual_seed(21)
+    for (b, n, k, c) in ((3, 1024, 20, 64), (2, 717, 20, 64), (2, 300, 5, 40), (1, 2048, 32, 128)):
+        x = cu(torch.rand(b, 3, n, generator=g) * 2 - 1)
+        conv = torch.nn.Conv2d(6, c, kernel_size=1, bias=False).cuda()
+        bn = torch.nn.BatchNorm2d(c).cuda()
+        with torch.no_grad():
+            bn.running_mean.copy_(cu(torch.randn(c, generator=g) * 0.2))
+            bn.running_var.copy_(cu(torch.rand(c, generator=g) + 0.5))
+            bn.weight.copy_(cu(torch.rand(c, generator=g) + 0.5))
+            bn.bias.copy_(cu(torch.randn(c, generator=g) * 0.1))
+        bn.eval()
+        idx = og.knn(x.transpose(1, 2), x.transpose(1, 2), k)
+        with torch.no_grad():
+            edge = og.get_graph_feature(x, k, idx)
+            ref_act = torch.relu(bn(conv(edge)))
+            ref_max = ref_act.max(dim=-1, keepdim=True)[0]
+        act, pooled = modules.edge_conv1(x, idx, conv, bn)
+        assert tuple(act.shape) == (b, c, n, k) and tuple(pooled.shape) == (b, c, n, 1) and act.is_contiguous()
+        e_act = float((act - ref_act).abs().max() / ref_act.abs().max())
+        e_max = float((pooled - ref_max).abs().max() / ref_max.abs().max())
+        print(f"\n  edge_conv1 N={n} k={k} C={c}: act {e_act:.2e}, max {e_max:.2e} relative")
+        assert e_act < 1e-5 and e_max < 1e-5
+        assert torch.equal(pooled, act.max(dim=-1, keepdim=True)[0]), "the pooled output is the max of the activations it wrote"
+        _, pooled_only = modules.edge_conv1(x, idx, conv, bn, want_act=False)
+        assert torch.equal(pooled_only, pooled)
+    bn.train()
+    with pytest.raises(RuntimeError, match="eval"):
+        modules.edge_conv1(x, idx, conv, bn)
+
+
 # ------------------------------------------------------------------------------------------ FPS
 def test_fps(og, orc, golden):
     g = golden("fps")

@@ -47,8 +47,8 @@ def select_stats(src, dst, k):
     v = st.cpu().tolist()
     w = max(v[1], 1)
     return {"warps": v[1], "redo_frac": v[0] / w, "steps_per_warp": v[2] / w, "merges_per_warp": v[3] / w,
-            "max_collected_per_warp": v[4] / w, "max_groups_per_warp": v[5] / w, "overflow_frac": v[6] / w,
-            "tie_frac": v[7] / w, "few_groups_frac": v[8] / w}
+            "insert_rounds_per_warp": v[4] / w, "max_groups_per_warp": v[5] / w, "tie_frac": v[7] / w,
+            "few_groups_frac": v[8] / w}
 
 
 def case(name, src, dst, k, edge, reps=20):
