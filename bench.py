@@ -558,7 +558,8 @@ def time_model_forward(dev, pairs=32, reps=3):
 
     def best_of():
         best = None
-        with torch.no_grad():
+        # cuDNN off in both arms, as the reference's own scripts run (train.py:194-196): FP32 convolutions, no TF32
+        with torch.no_grad(), torch.backends.cudnn.flags(enabled=False):
             for i in range(reps + 1):
                 torch.manual_seed(7)
                 torch.cuda.synchronize()
@@ -582,7 +583,7 @@ def time_model_forward(dev, pairs=32, reps=3):
             "rot_deg_patched_vs_reference": float(rot_err_deg(out_new[0].cpu(), out_ref[0].cpu()).max()),
             "overlap_score_abs_diff": float((out_new[2] - out_ref[2]).abs().max()),
             "note": "whole model incl. the PyTorch DGCNN convolutions and transformer overlap detector that stay PyTorch in "
-                    "both arms; random-init weights, eval(), no_grad, best of %d after 1 warm-up" % reps}
+                    "both arms; random-init weights, eval(), no_grad, cuDNN disabled as in train.py:194-196, best of %d after 1 warm-up" % reps}
 
 
 # ----------------------------------------------------------------------------------------- our arm

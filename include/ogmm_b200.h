@@ -169,6 +169,18 @@ int ogmm_gmm_moments_feat(const float* gamma, int64_t g_sb, int64_t g_sn, int64_
                           int64_t B, int64_t N, int64_t J, int64_t D,
                           float* pi_out, float* mu_out, ogmm_stream_t stream);
 
+/* ogmm_gmm_moments_feat with a scratch buffer, for few clouds with very many points (BASELINE.json configs[3]: the
+ * cloud x row-block items of 4 clouds leave most SMs idle): the points of a cloud are split over several CTAs whose raw
+ * sums a second kernel adds in a fixed order.  ogmm_gmm_moments_feat_workspace returns the bytes needed, 0 when the call
+ * gains nothing from the split (the _ws entry point then behaves exactly like ogmm_gmm_moments_feat; workspace may be
+ * NULL).  Results agree with the one-pass kernel to FP32 rounding (another summation order). */
+int64_t ogmm_gmm_moments_feat_workspace(int64_t B, int64_t N, int64_t J, int64_t D);
+int ogmm_gmm_moments_feat_ws(const float* gamma, int64_t g_sb, int64_t g_sn, int64_t g_sj,
+                             const float* feats, int64_t f_sb, int64_t f_sn, int64_t f_sd,
+                             int64_t B, int64_t N, int64_t J, int64_t D,
+                             float* pi_out, float* mu_out, void* workspace, int64_t workspace_bytes,
+                             ogmm_stream_t stream);
+
 /* Backward of ogmm_gmm_moments_feat with respect to the features (the reference reaches it
  * through autograd from lib/utils.py:289 in train.py:57-75, with gamma detached at lib/utils.py:286):
  *   grad_feats[b,n,d] = sum_j gamma[b,n,j] * grad_mu[b,j,d] / (pi[b,j] * N + 1e-5)

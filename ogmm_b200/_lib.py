@@ -44,6 +44,8 @@ SIGNATURES = {
     "ogmm_sinkhorn": (i32, [c_f, c_f, c_f, i64, i64, i64, f32, f32, i64, c_f, c_f, c_i32p, vp, i64, vp]),
     "ogmm_gmm_moments": (i32, [c_f, i64, i64, i64, c_f, i64, i64, i64, i64, i64, i64, i64, c_f, c_f, c_f, vp]),
     "ogmm_gmm_moments_feat": (i32, [c_f, i64, i64, i64, c_f, i64, i64, i64, i64, i64, i64, i64, c_f, c_f, vp]),
+    "ogmm_gmm_moments_feat_workspace": (i64, [i64, i64, i64, i64]),
+    "ogmm_gmm_moments_feat_ws": (i32, [c_f, i64, i64, i64, c_f, i64, i64, i64, i64, i64, i64, i64, c_f, c_f, vp, i64, vp]),
     "ogmm_gmm_moments_feat_backward": (i32, [c_f, i64, i64, i64, c_f, c_f, i64, i64, i64, i64, c_f, i64, i64, i64, vp]),
     "ogmm_softmax_moments": (i32, [c_f, c_f, i64, i64, i64, i64, i64, i64, c_f, c_f, c_f, c_f, vp]),
     "ogmm_rigid_transform": (i32, [c_f, i64, i64, i64, c_f, i64, i64, i64, c_f, i64, i64, i64, i64, c_f, c_f, vp]),

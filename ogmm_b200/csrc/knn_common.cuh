@@ -166,6 +166,10 @@ __device__ __forceinline__ void sort_pairs(float* key, int* val, int n) {
     }
 }
 
+// Axis key of a point for the CTA sort: NaN coordinates sort like +inf, so the comparator stays a total order and the
+// sorted order is a permutation of the cloud whatever the input holds (every query row gets written).
+__device__ __forceinline__ float sort_key(float v) { return v == v ? v : INFINITY; }
+
 __device__ __forceinline__ float sqn3(float x, float y, float z) {
     return __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
 }

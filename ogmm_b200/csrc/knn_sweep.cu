@@ -83,12 +83,12 @@ knn3_sweep_kernel(const float* __restrict__ src, int64_t s_sb, int64_t s_sn, int
 
     // ---- sort candidates along the axis ----------------------------------------------------------------------
     for (int m = tid; m < Mp; m += kSwThreads) {
-        s_ckey[m] = m < M ? db[(int64_t)m * d_sn + d_ax] : INFINITY;
+        s_ckey[m] = m < M ? sort_key(db[(int64_t)m * d_sn + d_ax]) : INFINITY;
         s_cord[m] = m < M ? m : 0x7fffffff;
     }
     if (!self)
         for (int n = tid; n < Np; n += kSwThreads) {
-            s_qkey[n] = n < N ? sb[(int64_t)n * s_sn + s_ax] : INFINITY;
+            s_qkey[n] = n < N ? sort_key(sb[(int64_t)n * s_sn + s_ax]) : INFINITY;
             s_qord[n] = n < N ? n : 0x7fffffff;
         }
     __syncthreads();

@@ -169,7 +169,8 @@ template <int JP, int DT>
 __global__ void __launch_bounds__(kFeatThreads, (DT * JP <= 32) ? 3 : ((DT * JP <= 64) ? 2 : 1))
 gmm_moments_feat_kernel(const float* __restrict__ gamma, int64_t g_sb, int64_t g_sn, int64_t g_sj,
                         const float* __restrict__ feats, int64_t f_sb, int64_t f_sn, int64_t f_sd,
-                        int N, int J, int D, float* __restrict__ pi_out, float* __restrict__ mu_out) {
+                        int N, int J, int D, float* __restrict__ pi_out, float* __restrict__ mu_out,
+                        int n_per_split, float* __restrict__ part_sum, float* __restrict__ part_gs) {
     using C = FeatCfg<JP, DT>;
     constexpr int TD = C::TD, PITCH = C::PITCH;
     extern __shared__ __align__(16) float sm[];
@@ -181,6 +182,10 @@ gmm_moments_feat_kernel(const float* __restrict__ gamma, int64_t g_sb, int64_t g
 
     const int b = blockIdx.y, d0 = blockIdx.x * TD;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // split mode (part_sum != nullptr): blockIdx.z owns points [n_lo, n_hi) and writes RAW sums; a fold kernel adds the
+    // splits in order and normalises (few clouds with very many points: cloud x row-block items alone leave SMs idle)
+    const int n_lo = part_sum ? (int)blockIdx.z * n_per_split : 0;
+    const int n_hi = part_sum ? min(N, n_lo + n_per_split) : N;
     const float* g = gamma + (int64_t)b * g_sb;
     const float* f = feats + (int64_t)b * f_sb;
 
@@ -204,7 +209,7 @@ gmm_moments_feat_kernel(const float* __restrict__ gamma, int64_t g_sb, int64_t g
     constexpr int GQ = (kTN * JP / 4 + kFeatThreads - 1) / kFeatThreads;      // gamma float4s per thread per stage
     float4 gr[GQ];
     auto ldg_stage = [&](int n0) {
-        if (f_fast && n0 + kTN <= N) {
+        if (f_fast && n0 + kTN <= n_hi) {
 #pragma unroll
             for (int k = 0; k < DT; ++k) {
                 const int u = tid + kFeatThreads * k;
@@ -213,7 +218,7 @@ gmm_moments_feat_kernel(const float* __restrict__ gamma, int64_t g_sb, int64_t g
                 fr[k] = ldg_stream4(f + (int64_t)(d0 + row) * f_sd + n0 + 4 * chunk);
             }
         }
-        if (g_fast && n0 + kTN <= N) {
+        if (g_fast && n0 + kTN <= n_hi) {
 #pragma unroll
             for (int q = 0; q < GQ; ++q)
                 if (tid + kFeatThreads * q < kTN * JP / 4)
@@ -223,7 +228,7 @@ gmm_moments_feat_kernel(const float* __restrict__ gamma, int64_t g_sb, int64_t g
     auto sts_stage = [&](int n0, int slot) {
         float* fs = s_f + slot * C::F_STAGE;
         float* gs = s_g + slot * C::G_STAGE;
-        if (f_fast && n0 + kTN <= N) {
+        if (f_fast && n0 + kTN <= n_hi) {
 #pragma unroll
             for (int k = 0; k < DT; ++k) {
                 const int u = tid + kFeatThreads * k;
@@ -239,11 +244,11 @@ gmm_moments_feat_kernel(const float* __restrict__ gamma, int64_t g_sb, int64_t g
                 int n, r;
                 if (d_fastest) { n = e / TD; r = e - n * TD; } else { r = e / kTN; n = e - r * kTN; }
                 float v = 0.f;
-                if (n0 + n < N && d0 + r < D) v = ldg_stream(f + (int64_t)(n0 + n) * f_sn + (int64_t)(d0 + r) * f_sd);
+                if (n0 + n < n_hi && d0 + r < D) v = ldg_stream(f + (int64_t)(n0 + n) * f_sn + (int64_t)(d0 + r) * f_sd);
                 fs[n * PITCH + r] = v;
             }
         }
-        if (g_fast && n0 + kTN <= N) {
+        if (g_fast && n0 + kTN <= n_hi) {
 #pragma unroll
             for (int q = 0; q < GQ; ++q)
                 if (tid + kFeatThreads * q < kTN * JP / 4) *reinterpret_cast<float4*>(gs + 4 * (tid + kFeatThreads * q)) = gr[q];
@@ -251,7 +256,7 @@ gmm_moments_feat_kernel(const float* __restrict__ gamma, int64_t g_sb, int64_t g
             for (int e = tid; e < kTN * JP; e += kFeatThreads) {
                 const int n = e / JP, j = e - n * JP;
                 float v = 0.f;
-                if (n0 + n < N && j < J) v = g[(int64_t)(n0 + n) * g_sn + (int64_t)j * g_sj];
+                if (n0 + n < n_hi && j < J) v = g[(int64_t)(n0 + n) * g_sn + (int64_t)j * g_sj];
                 gs[e] = v;
             }
         }
@@ -261,21 +266,23 @@ gmm_moments_feat_kernel(const float* __restrict__ gamma, int64_t g_sb, int64_t g
     // loads of the next stage then hit L2 (~300 cycles) instead of HBM (~800+), which one stage of FMAs covers.
     constexpr int kPF = 6;
     auto prefetch_stage = [&](int n0) {
-        if (f_fast && n0 + kTN <= N) {
+        if (f_fast && n0 + kTN <= n_hi) {
             for (int r = tid; r < TD; r += kFeatThreads)
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(f + (int64_t)(d0 + r) * f_sd + n0));
         }
     };
-    const int n_stages = (N + kTN - 1) / kTN;
+    const int n_stages = (max(n_hi - n_lo, 0) + kTN - 1) / kTN;
 #pragma unroll 1
-    for (int s = 1; s <= kPF && s < n_stages; ++s) prefetch_stage(s * kTN);
-    ldg_stage(0);
-    sts_stage(0, 0);
+    for (int s = 1; s <= kPF && s < n_stages; ++s) prefetch_stage(n_lo + s * kTN);
+    if (n_stages > 0) {
+        ldg_stage(n_lo);
+        sts_stage(n_lo, 0);
+    }
     __syncthreads();
     for (int s = 0; s < n_stages; ++s) {
         const int slot = s & 1;
-        if (s + 1 < n_stages) ldg_stage((s + 1) * kTN);
-        if (s + 1 + kPF < n_stages) prefetch_stage((s + 1 + kPF) * kTN);
+        if (s + 1 < n_stages) ldg_stage(n_lo + (s + 1) * kTN);
+        if (s + 1 + kPF < n_stages) prefetch_stage(n_lo + (s + 1 + kPF) * kTN);
         const float* fs = s_f + slot * C::F_STAGE;
         const float* gs = s_g + slot * C::G_STAGE;
 #pragma unroll
@@ -298,7 +305,7 @@ gmm_moments_feat_kernel(const float* __restrict__ gamma, int64_t g_sb, int64_t g
                 }
             }
         }
-        if (s + 1 < n_stages) sts_stage((s + 1) * kTN, slot ^ 1);
+        if (s + 1 < n_stages) sts_stage(n_lo + (s + 1) * kTN, slot ^ 1);
         __syncthreads();
     }
 
@@ -313,7 +320,9 @@ gmm_moments_feat_kernel(const float* __restrict__ gamma, int64_t g_sb, int64_t g
         for (int w = 0; w < 8; ++w) t += s_gs[w * JP + tid];
         const float pi = __fdiv_rn(t, (float)N);
         s_npi[tid] = __fadd_rn(__fmul_rn(pi, (float)N), 1e-5f);
-        if (blockIdx.x == 0 && tid < J && pi_out) pi_out[(int64_t)b * J + tid] = pi;
+        if (part_sum) {
+            if (blockIdx.x == 0 && tid < J) part_gs[((int64_t)b * gridDim.z + blockIdx.z) * J + tid] = t;
+        } else if (blockIdx.x == 0 && tid < J && pi_out) pi_out[(int64_t)b * J + tid] = pi;
     }
     // ---- fold the 8 warps' partial sums: 4 -> 0..3, then 2,3 -> 0,1, then 1 -> 0 (buffer aliases the stages) --
     // layout of one warp's block: [j][TD] with d = lane + 32 i contiguous across lanes
@@ -348,12 +357,38 @@ gmm_moments_feat_kernel(const float* __restrict__ gamma, int64_t g_sb, int64_t g
             for (int i = 0; i < DT; ++i) {
                 const int d = d0 + lane + 32 * i;
                 if (d < D) {
-                    if (2 * j < J) mu_out[((int64_t)b * J + 2 * j) * D + d] = __fdiv_rn(acc[i][j].x, s_npi[2 * j]);
-                    if (2 * j + 1 < J) mu_out[((int64_t)b * J + 2 * j + 1) * D + d] = __fdiv_rn(acc[i][j].y, s_npi[2 * j + 1]);
+                    if (part_sum) {
+                        float* ps = part_sum + ((int64_t)b * gridDim.z + blockIdx.z) * J * D;
+                        if (2 * j < J) ps[(int64_t)(2 * j) * D + d] = acc[i][j].x;
+                        if (2 * j + 1 < J) ps[(int64_t)(2 * j + 1) * D + d] = acc[i][j].y;
+                    } else {
+                        if (2 * j < J) mu_out[((int64_t)b * J + 2 * j) * D + d] = __fdiv_rn(acc[i][j].x, s_npi[2 * j]);
+                        if (2 * j + 1 < J) mu_out[((int64_t)b * J + 2 * j + 1) * D + d] = __fdiv_rn(acc[i][j].y, s_npi[2 * j + 1]);
+                    }
                 }
             }
         }
     }
+}
+
+// =====================================================================================================
+// Fold of the split mode: adds the splits' raw sums in split order (deterministic) and normalises like the one-pass kernel.
+__global__ void __launch_bounds__(256)
+gmm_moments_feat_fold_kernel(const float* __restrict__ part_sum, const float* __restrict__ part_gs, int S, int N, int J, int D,
+                             float* __restrict__ pi_out, float* __restrict__ mu_out) {
+    const int b = blockIdx.y;
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // (j, d)
+    if (e >= (int64_t)J * D) return;
+    const int j = (int)(e / D);
+    float t = 0.f, a = 0.f;
+    for (int s = 0; s < S; ++s) {
+        t += part_gs[((int64_t)b * S + s) * J + j];
+        a += part_sum[((int64_t)b * S + s) * J * D + e];
+    }
+    const float pi = __fdiv_rn(t, (float)N);
+    const float npi = __fadd_rn(__fmul_rn(pi, (float)N), 1e-5f);
+    mu_out[(int64_t)b * J * D + e] = __fdiv_rn(a, npi);
+    if (e - (int64_t)j * D == 0 && pi_out) pi_out[(int64_t)b * J + j] = pi;
 }
 
 // =====================================================================================================
@@ -536,6 +571,43 @@ int ogmm_launch_moments_feat_tc(const float* gamma, int64_t g_sb, int64_t g_sn, 
                                 const float* feats, int64_t f_sb, int64_t f_sn, int64_t f_sd,
                                 int64_t B, int64_t N, int64_t J, int64_t D, float* pi_out, float* mu_out, cudaStream_t s);
 
+// FP32 FFMA2 kernel for every shape; splits > 1: split mode + fold (see feat_splits below).
+static int launch_feat_generic(const float* gamma, int64_t g_sb, int64_t g_sn, int64_t g_sj,
+                               const float* feats, int64_t f_sb, int64_t f_sn, int64_t f_sd,
+                               int64_t B, int64_t N, int64_t J, int64_t D, float* pi_out, float* mu_out,
+                               int splits, float* part_sum, float* part_gs, cudaStream_t s) {
+    // points per split: a multiple of the stage size, so only the last split of a cloud sees a ragged tile
+    const int n_per = splits > 1 ? (int)(((N + splits - 1) / splits + kTN - 1) / kTN * kTN) : (int)N;
+#define LAUNCH(JP, DT)                                                                                              \
+    do {                                                                                                            \
+        using C = FeatCfg<JP, DT>;                                                                                  \
+        if (C::SMEM > 48 * 1024) {                                                                                  \
+            int st = cuda_status(cudaFuncSetAttribute(gmm_moments_feat_kernel<JP, DT>,                              \
+                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM),   \
+                                 "cudaFuncSetAttribute(gmm_moments_feat_kernel)");                                  \
+            if (st != OGMM_OK) return st;                                                                           \
+        }                                                                                                           \
+        dim3 grid((unsigned)((D + C::TD - 1) / C::TD), (unsigned)B, (unsigned)splits);                              \
+        gmm_moments_feat_kernel<JP, DT><<<grid, kFeatThreads, C::SMEM, s>>>(gamma, g_sb, g_sn, g_sj, feats, f_sb,   \
+                                                                            f_sn, f_sd, (int)N, (int)J, (int)D,     \
+                                                                            pi_out, mu_out, n_per,                  \
+                                                                            splits > 1 ? part_sum : nullptr,        \
+                                                                            part_gs);                               \
+    } while (0)
+    if (J <= 16) LAUNCH(16, 4);
+    else if (J <= 32) LAUNCH(32, 2);
+    else if (J <= 64) LAUNCH(64, 1);
+    else LAUNCH(128, 1);
+#undef LAUNCH
+    OGMM_LAUNCH_CHECK("gmm_moments_feat_kernel");
+    if (splits > 1) {
+        dim3 grid((unsigned)((J * D + 255) / 256), (unsigned)B);
+        gmm_moments_feat_fold_kernel<<<grid, 256, 0, s>>>(part_sum, part_gs, splits, (int)N, (int)J, (int)D, pi_out, mu_out);
+        OGMM_LAUNCH_CHECK("gmm_moments_feat_fold_kernel");
+    }
+    return OGMM_OK;
+}
+
 extern "C" __attribute__((visibility("default"))) int ogmm_gmm_moments_feat(const float* gamma, int64_t g_sb, int64_t g_sn, int64_t g_sj,
                                      const float* feats, int64_t f_sb, int64_t f_sn, int64_t f_sd,
                                      int64_t B, int64_t N, int64_t J, int64_t D,
@@ -568,27 +640,45 @@ extern "C" __attribute__((visibility("default"))) int ogmm_gmm_moments_feat(cons
             if (st != OGMM_EUNSUPPORTED) return st;
         }
     }
-#define LAUNCH(JP, DT)                                                                                              \
-    do {                                                                                                            \
-        using C = FeatCfg<JP, DT>;                                                                                  \
-        if (C::SMEM > 48 * 1024) {                                                                                  \
-            int st = cuda_status(cudaFuncSetAttribute(gmm_moments_feat_kernel<JP, DT>,                              \
-                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM),   \
-                                 "cudaFuncSetAttribute(gmm_moments_feat_kernel)");                                  \
-            if (st != OGMM_OK) return st;                                                                           \
-        }                                                                                                           \
-        dim3 grid((unsigned)((D + C::TD - 1) / C::TD), (unsigned)B);                                                \
-        gmm_moments_feat_kernel<JP, DT><<<grid, kFeatThreads, C::SMEM, s>>>(gamma, g_sb, g_sn, g_sj, feats, f_sb,   \
-                                                                            f_sn, f_sd, (int)N, (int)J, (int)D,     \
-                                                                            pi_out, mu_out);                        \
-    } while (0)
-    if (J <= 16) LAUNCH(16, 4);
-    else if (J <= 32) LAUNCH(32, 2);
-    else if (J <= 64) LAUNCH(64, 1);
-    else LAUNCH(128, 1);
-#undef LAUNCH
-    OGMM_LAUNCH_CHECK("gmm_moments_feat_kernel");
-    return OGMM_OK;
+    return launch_feat_generic(gamma, g_sb, g_sn, g_sj, feats, f_sb, f_sn, f_sd, B, N, J, D, pi_out, mu_out, 1, nullptr, nullptr, s);
+}
+
+// Split mode for few clouds with very many points (BASELINE.json configs[3]: 4 clouds x 16384 points give 64 CTAs of
+// cloud x row-block items on 148 SMs): the points of a cloud are divided over `splits` CTAs per row block, raw sums go
+// to the workspace and a fold kernel adds them in split order.  ogmm_gmm_moments_feat_workspace returns 0 when the
+// one-pass kernels already fill the GPU.
+static int64_t feat_splits(int64_t B, int64_t N, int64_t J, int64_t D) {
+    const int64_t td = J <= 16 ? 128 : (J <= 32 ? 64 : 32);
+    const int64_t ctas = B * ((D + td - 1) / td);
+    if (J <= 16 || N < 4096 || ctas >= 2 * 148) return 1;
+    int64_t sp = (2 * 148 + ctas - 1) / ctas;
+    if (sp > N / 2048) sp = N / 2048;
+    return sp < 1 ? 1 : sp;
+}
+
+extern "C" __attribute__((visibility("default"))) int64_t ogmm_gmm_moments_feat_workspace(int64_t B, int64_t N, int64_t J, int64_t D) {
+    if (B < 1 || N < 1 || J < 1 || D < 1) return 0;
+    const int64_t sp = feat_splits(B, N, J, D);
+    return sp <= 1 ? 0 : 4 * B * sp * (J * D + J);
+}
+
+extern "C" __attribute__((visibility("default"))) int ogmm_gmm_moments_feat_ws(const float* gamma, int64_t g_sb, int64_t g_sn, int64_t g_sj,
+                                                                             const float* feats, int64_t f_sb, int64_t f_sn, int64_t f_sd,
+                                                                             int64_t B, int64_t N, int64_t J, int64_t D,
+                                                                             float* pi_out, float* mu_out, void* workspace,
+                                                                             int64_t workspace_bytes, ogmm_stream_t stream) {
+    const int64_t need = ogmm_gmm_moments_feat_workspace(B, N, J, D);
+    if (need == 0 || workspace == nullptr)
+        return ogmm_gmm_moments_feat(gamma, g_sb, g_sn, g_sj, feats, f_sb, f_sn, f_sd, B, N, J, D, pi_out, mu_out, stream);
+    OGMM_REQUIRE(B < 65536 && J <= 128, OGMM_EUNSUPPORTED, "ogmm_gmm_moments_feat_ws: B=%lld J=%lld", (long long)B, (long long)J);
+    OGMM_REQUIRE(workspace_bytes >= need, OGMM_EWORKSPACE, "ogmm_gmm_moments_feat_ws: workspace of %lld B given, %lld B needed",
+                 (long long)workspace_bytes, (long long)need);
+    OGMM_REQUIRE(gamma && feats && mu_out, OGMM_EINVAL, "ogmm_gmm_moments_feat_ws: null pointer");
+    const int64_t sp = feat_splits(B, N, J, D);
+    float* part_sum = static_cast<float*>(workspace);
+    float* part_gs = part_sum + B * sp * J * D;
+    return launch_feat_generic(gamma, g_sb, g_sn, g_sj, feats, f_sb, f_sn, f_sd, B, N, J, D, pi_out, mu_out, (int)sp, part_sum, part_gs,
+                               as_stream(stream));
 }
 
 extern "C" __attribute__((visibility("default"))) int ogmm_gmm_moments(const float* gamma, int64_t g_sb, int64_t g_sn, int64_t g_sj,

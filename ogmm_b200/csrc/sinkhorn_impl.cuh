@@ -884,7 +884,7 @@ sinkhorn_kernel(SinkhornParams P, int mode) {
 using namespace ogmm;
 
 // ---- dispatch helpers --------------------------------------------------------------------------------------
-// (threads per CTA, points per thread) by cloud size.  N > 8192 needs the multi-CTA variant (not built yet).
+// (threads per CTA, points per thread) by cloud size.  N > 8192: the 16-CTA cluster variant (cluster_dsmem.cu).
 #define OGMM_DISPATCH_POINTS(N, CALL)                                   \
     do {                                                                \
         if ((N) <= 256)        { CALL(256, 1); }                        \
@@ -896,10 +896,10 @@ using namespace ogmm;
     } while (0)
 
 constexpr int64_t kMaxPoints = 8192;
-constexpr int64_t kMaxClusterPoints = 16384;      // clustering only: one extra (1024 threads x 16 points) variant
+constexpr int64_t kMaxClusterPoints = 16384;      // clustering only: 16-CTA cluster variant (cluster_dsmem.cu)
 
-// defined in cluster_big.cu (its own translation unit: the 16-points-per-thread body is slow to compile)
-int ogmm_launch_cluster_big(ogmm::SinkhornParams P, cudaStream_t s);
+// defined in cluster_dsmem.cu: clouds of 8193..16384 points, one cloud per 16-CTA thread-block cluster
+int ogmm_launch_cluster_dsmem(ogmm::SinkhornParams P, cudaStream_t s);
 
 template <int NT, int PPT, bool kCluster, bool kFast, bool kExactJ = false>
 static inline int launch_sinkhorn_variant(SinkhornParams P, cudaStream_t s) {
@@ -932,7 +932,7 @@ static inline int launch_sinkhorn(SinkhornParams P, void* workspace, int64_t wor
     int st = cuda_status(cudaMemsetAsync(ws, 0, 64, s), "cudaMemsetAsync(workspace header)");
     if (st != OGMM_OK) return st;
     if constexpr (kCluster) {
-        if (P.N > kMaxPoints) return ogmm_launch_cluster_big(P, s);
+        if (P.N > kMaxPoints) return ogmm_launch_cluster_dsmem(P, s);
         if (P.J <= 16 && P.N <= 1024) {
             if (P.N <= 256) return launch_sinkhorn_variant<256, 1, true, true>(P, s);
             if (P.N <= 512) return launch_sinkhorn_variant<256, 2, true, true>(P, s);

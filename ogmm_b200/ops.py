@@ -200,8 +200,10 @@ def gmm_moments(gamma, pts, return_sigma=False):
         else:
             if return_sigma:
                 raise NotImplementedError("gmm_moments: sigma is built for D <= 4 (the reference only uses it on xyz)")
-            st = lib.ogmm_gmm_moments_feat(gamma.data_ptr(), *gamma.stride(), pts.data_ptr(), *pts.stride(), B, N, J, D,
-                                           pi.data_ptr(), mu.data_ptr(), _stream(gamma))
+            nbytes = int(lib.ogmm_gmm_moments_feat_workspace(B, N, J, D))       # > 0: few clouds, very many points
+            ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev) if nbytes > 0 else None
+            st = lib.ogmm_gmm_moments_feat_ws(gamma.data_ptr(), *gamma.stride(), pts.data_ptr(), *pts.stride(), B, N, J, D,
+                                              pi.data_ptr(), mu.data_ptr(), _ptr(ws), nbytes, _stream(gamma))
             what = "ogmm_gmm_moments_feat"
     _lib.check(st, what)
     return (pi, mu, sigma) if return_sigma else (pi, mu)

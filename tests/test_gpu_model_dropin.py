@@ -39,7 +39,8 @@ def _pairs(nb, n, seed=0):
 
 def _run(model, src, tgt, seed):
     torch.manual_seed(seed)
-    with torch.no_grad():
+    # cuDNN off as in the reference's own scripts (train.py:194-196): convolutions in plain FP32, not cuDNN's TF32
+    with torch.no_grad(), torch.backends.cudnn.flags(enabled=False):
         out = model(src, tgt)
     torch.cuda.synchronize()
     return out
