@@ -19,6 +19,8 @@
 //     candidates are re-ranked with exact FP32 distances (FMA chain over c, the generic kernel's arithmetic).
 //     The superset is buffered per selector thread and drained into a sorted exact list whenever the buffer fills,
 //     so its size is unbounded and the result never depends on the tensor-core rounding.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -369,6 +371,11 @@ static size_t wide_smem_bytes(int C, int BN, int cap, int K) {
 
 using namespace ogmm;
 
+int ogmm_launch_knn_wide2(const float* src, int64_t s_sb, int64_t s_sn, int64_t s_sc,
+                          const float* dst, int64_t d_sb, int64_t d_sn, int64_t d_sc,
+                          int64_t B, int64_t N, int64_t M, int64_t C, int64_t k, int normalize,
+                          int64_t* idx_out, float* dist_out, int32_t* stats, cudaStream_t s);
+
 // Called by ogmm_knn_graph / ogmm_knn_wide for 32 <= C <= 256.  `stats` (device int32, may be null) counts the
 // queries that needed the exhaustive fallback.
 int ogmm_launch_knn_wide(const float* src, int64_t s_sb, int64_t s_sn, int64_t s_sc,
@@ -376,6 +383,16 @@ int ogmm_launch_knn_wide(const float* src, int64_t s_sb, int64_t s_sn, int64_t s
                          int64_t B, int64_t N, int64_t M, int64_t C, int64_t k, int normalize,
                          int64_t* idx_out, float* dist_out, int32_t* stats, cudaStream_t s) {
     OGMM_REQUIRE(k <= 32, OGMM_EUNSUPPORTED, "knn (tensor-core path): k=%lld > 32", (long long)k);
+    // pipelined one-pass kernel (knn_wide2.cu) where it applies (C <= 128, M <= 65535); OGMM_KNN_WIDE_V1=1 keeps this
+    // file's two-pass kernel for A/B timing (bit-identical results)
+    {
+        const char* v1 = getenv("OGMM_KNN_WIDE_V1");
+        if (!(v1 && v1[0] == '1')) {
+            const int st2 = ogmm_launch_knn_wide2(src, s_sb, s_sn, s_sc, dst, d_sb, d_sn, d_sc, B, N, M, C, k, normalize, idx_out,
+                                                  dist_out, stats, s);
+            if (st2 != OGMM_EUNSUPPORTED) return st2;
+        }
+    }
     // candidate tile and superset buffer: two CTAs per SM when they fit (selection is latency bound, it wants warps),
     // else the largest tile that fits one CTA
     const int K = k <= 8 ? 8 : (k <= 16 ? 16 : (k <= 20 ? 20 : 32));

@@ -19,13 +19,14 @@ for c in args.cs:
     g = torch.Generator().manual_seed(c)
     x = torch.relu(torch.randn(args.b, args.n, c, generator=g)).to(dev)
     res = {"C": c, "N": args.n, "B": args.b, "k": args.k}
-    for name, env in (("tensor_core", None), ("fp32_fma", "1")):
-        if env and args.skip_fp32:
+    # tensor_core = the pipelined one-pass kernel (knn_wide2.cu) where it applies, tensor_core_v1 = the two-pass kernel
+    for name, var in (("tensor_core", None), ("tensor_core_v1", "OGMM_KNN_WIDE_V1"), ("fp32_fma", "OGMM_KNN_NO_TENSOR")):
+        if name == "fp32_fma" and args.skip_fp32:
             continue
-        if env:
-            os.environ["OGMM_KNN_NO_TENSOR"] = env
-        else:
-            os.environ.pop("OGMM_KNN_NO_TENSOR", None)
+        os.environ.pop("OGMM_KNN_NO_TENSOR", None)
+        os.environ.pop("OGMM_KNN_WIDE_V1", None)
+        if var:
+            os.environ[var] = "1"
         for _ in range(2):
             idx = og.knn(x, x, args.k)
         torch.cuda.synchronize()
@@ -38,11 +39,16 @@ for c in args.cs:
         ms = e0.elapsed_time(e1) / args.reps
         flops = 2.0 * args.b * args.n * args.n * c
         res[name] = {"ms": ms, "gram_tflops": flops / ms / 1e9, "clouds_per_s": args.b / ms * 1e3}
-        res[name + "_idx_sum"] = int(idx.sum())
+        res[name + "_idx"] = idx
     os.environ.pop("OGMM_KNN_NO_TENSOR", None)
+    os.environ.pop("OGMM_KNN_WIDE_V1", None)
     if "fp32_fma" in res:
         res["speedup"] = res["fp32_fma"]["ms"] / res["tensor_core"]["ms"]
-        res["identical"] = res["tensor_core_idx_sum"] == res["fp32_fma_idx_sum"]
+        res["speedup_v1"] = res["fp32_fma"]["ms"] / res["tensor_core_v1"]["ms"]
+        res["identical"] = bool(torch.equal(res["tensor_core_idx"], res["fp32_fma_idx"]))
+        res["identical_v1"] = bool(torch.equal(res["tensor_core_v1_idx"], res["fp32_fma_idx"]))
+    for nm in ("tensor_core", "tensor_core_v1", "fp32_fma"):
+        res.pop(nm + "_idx", None)
     fb = og.ops.knn_wide(x, x, args.k)[2]
     res["fallback_queries"] = int(fb)
     out.append(res)
