@@ -32,8 +32,8 @@
 namespace ogmm {
 
 constexpr int kW2Q = 128;               // queries per CTA = MMA M = TMEM lanes
-constexpr int kW2Threads = 384;         // warp 0 TMA, warp 1 MMA, warps 2-3 idle, warps 4..11 selectors
-constexpr int kW2Sel = 256;             // selector threads (two per query)
+// threads: warp 0 TMA, warp 1 MMA, warps 2-3 idle, then SEL selector threads per query (SEL = 2: warps 4..11, the two
+// threads of a query split every tile's columns; SEL = 1 when the operand tiles leave no room for 256 collect columns)
 constexpr int kW2Aug = 8;               // extra K columns of the augmented operands
 constexpr int kW2Stage = 12;            // staging slots per selector thread
 constexpr int kW2Trigger = 4;           // merge when a lane holds more than this many (room for one more group of 8)
@@ -49,6 +49,16 @@ constexpr u64x kW2Empty = (0xff800000ull << 32) | 0xffffffffull;
 
 __device__ __forceinline__ void w2_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// wait of the single-lane roles: back off between polls so the two spinning lanes leave the issue slots to the selectors
+__device__ __forceinline__ void w2_wait_idle(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    while (true) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (ok) break;
+        __nanosleep(64);
+    }
 }
 __device__ __forceinline__ void w2_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -100,6 +110,34 @@ __device__ __forceinline__ float w2_exact_dist(const float* __restrict__ x, int6
     return fmaxf(__fadd_rn(__fadd_rn(acc, qn), cn), 1e-12f);
 }
 
+// The same value from the staged query tile and 16-byte candidate loads: the tile holds -2 x (exact scaling), and
+// fma(-2 x, y, acc) == fma(x, -2 y, acc) bit for bit; |y|^2 is summed in the same order as above.  Eight loads are in
+// flight per batch instead of one dependent global load per feature.
+__device__ __noinline__ float w2_exact_dist_fast(const unsigned char* __restrict__ sA, int ql, const float* __restrict__ y,
+                                                    int C, float qn, int normalize) {
+    float acc = 0.f, cn = 0.f;
+    const float4* y4 = reinterpret_cast<const float4*>(y);
+    for (int c0 = 0; c0 < C; c0 += 32) {                        // one 128-byte K-block of the tile per batch
+        float4 yv[8];
+        const int nch = min(8, (C - c0) >> 2);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) if (u < nch) yv[u] = __ldg(y4 + (c0 >> 2) + u);
+        const unsigned char* blk = sA + (size_t)(c0 >> 5) * kW2Q * 128;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (u < nch) {
+                const float4 xa = *reinterpret_cast<const float4*>(blk + sw128_off(ql, u));
+                acc = fmaf(xa.x, yv[u].x, acc); cn = __fadd_rn(cn, __fmul_rn(yv[u].x, yv[u].x));
+                acc = fmaf(xa.y, yv[u].y, acc); cn = __fadd_rn(cn, __fmul_rn(yv[u].y, yv[u].y));
+                acc = fmaf(xa.z, yv[u].z, acc); cn = __fadd_rn(cn, __fmul_rn(yv[u].z, yv[u].z));
+                acc = fmaf(xa.w, yv[u].w, acc); cn = __fadd_rn(cn, __fmul_rn(yv[u].w, yv[u].w));
+            }
+        }
+    }
+    if (normalize) return __fadd_rn(acc, 2.0f);
+    return fmaxf(__fadd_rn(__fadd_rn(acc, qn), cn), 1e-12f);
+}
+
 template <int K>
 __device__ __forceinline__ void w2_key_insert(u64x (&key)[K], u64x kv) {
     if (!(kv < key[K - 1])) return;
@@ -121,18 +159,19 @@ struct Wide2Args {
     int64_t* idx_out; float* dist_out; int32_t* stats;
 };
 
-template <int K>
-__global__ void __launch_bounds__(kW2Threads, 1)
+template <int K, int SEL>
+__global__ void __launch_bounds__(128 + 128 * SEL, 1)
 knn_wide2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_c, Wide2Args a) {
     extern __shared__ __align__(16) unsigned char w2_raw[];
     unsigned char* sm = w2_raw + ((1024u - (smem_u32(w2_raw) & 1023u)) & 1023u);      // SWIZZLE_128B atoms: 1024-byte aligned
+    constexpr int kW2Sel = 128 * SEL;
     const int BN = a.BN, KB = a.KB;
     const uint32_t a_bytes = (uint32_t)KB * kW2Q * 128, b_bytes = (uint32_t)KB * BN * 128;
     unsigned char* sA = sm;
     unsigned char* sB = sA + a_bytes;                                                  // [2][KB][BN x 128 B]
-    float* s_stage_v = reinterpret_cast<float*>(sB + 2 * b_bytes);                     // [kW2Stage][256]
-    unsigned short* s_stage_i = reinterpret_cast<unsigned short*>(s_stage_v + kW2Stage * kW2Sel);
-    float* s_col_v = reinterpret_cast<float*>(s_stage_i + kW2Stage * kW2Sel);          // [kW2Cap][256]
+    float* s_stage_v = reinterpret_cast<float*>(sB + 2 * b_bytes);                     // [kW2Stage][SEL x 128] values ...
+    int* s_stage_i = reinterpret_cast<int*>(s_stage_v + kW2Stage * kW2Sel);            // ... and indices, same stride
+    float* s_col_v = reinterpret_cast<float*>(s_stage_i + kW2Stage * kW2Sel);          // [kW2Cap][SEL x 128]
     unsigned short* s_col_i = reinterpret_cast<unsigned short*>(s_col_v + kW2Cap * kW2Sel);
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_col_i + kW2Cap * kW2Sel);          // full_a, full_b[2], empty_b[2], tfull[2], tempty[2]
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 9);
@@ -143,7 +182,7 @@ knn_wide2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
 
     if (tid == 0) {
         mbar_init(full_a, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(full_b + i, 1); mbar_init(empty_b + i, 1); mbar_init(tfull + i, 1); mbar_init(tempty + i, 8); }
+        for (int i = 0; i < 2; ++i) { mbar_init(full_b + i, 1); mbar_init(empty_b + i, 1); mbar_init(tfull + i, 1); mbar_init(tempty + i, 4 * SEL); }
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c) : "memory");
     }
@@ -160,7 +199,7 @@ knn_wide2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             for (int kb = 0; kb < KB; ++kb) w2_tma_3d(smem_u32(sA) + kb * kW2Q * 128, &map_q, kb * 32, q0, b, full_a);
             for (int t = 0; t < n_tiles; ++t) {
                 const int s = t & 1;
-                mbar_wait(empty_b + s, ((t >> 1) & 1) ^ 1);                 // first use of a slot passes at once
+                w2_wait_idle(empty_b + s, ((t >> 1) & 1) ^ 1);              // first use of a slot passes at once
                 w2_expect_tx(full_b + s, b_bytes);
                 for (int kb = 0; kb < KB; ++kb)
                     w2_tma_3d(smem_u32(sB) + s * b_bytes + kb * BN * 128, &map_c, kb * 32, t * BN, b, full_b + s);
@@ -171,11 +210,11 @@ knn_wide2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         if (lane == 0) {
             const uint32_t idesc = make_idesc_tf32(kW2Q, BN);
             const int ksteps = (a.C + kW2Aug + 7) / 8;                     // 8 TF32 columns per instruction
-            mbar_wait(full_a, 0);
+            w2_wait_idle(full_a, 0);
             for (int t = 0; t < n_tiles; ++t) {
                 const int s = t & 1;
-                mbar_wait(full_b + s, (t >> 1) & 1);
-                mbar_wait(tempty + s, ((t >> 1) & 1) ^ 1);                  // selectors are done with this TMEM buffer
+                w2_wait_idle(full_b + s, (t >> 1) & 1);
+                w2_wait_idle(tempty + s, ((t >> 1) & 1) ^ 1);               // selectors are done with this TMEM buffer
                 tc_fence_after();
                 for (int ks = 0; ks < ksteps; ++ks) {
                     const int kb = ks >> 2, kk = ks & 3;
@@ -196,6 +235,7 @@ knn_wide2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         const float* sb = a.src + (int64_t)b * a.s_sb;
         const float* db = a.dst + (int64_t)b * a.d_sb;
         const float* x = sb + (int64_t)(valid ? q : 0) * a.s_sn;
+        const bool y_vec = (a.d_sc == 1) && ((a.d_sn & 3) == 0) && ((a.d_sb & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.dst) & 15) == 0);
         float qn = 0.f;
         if (!a.normalize)
             for (int c = 0; c < a.C; ++c) { const float v = x[(int64_t)c * a.s_sc]; qn = __fadd_rn(qn, __fmul_rn(v, v)); }
@@ -211,12 +251,13 @@ knn_wide2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         float bound = valid ? 3.0e38f : -INFINITY;      // collect bound: best[K-1] + 2E (finite so that padding +inf never passes)
         int n_st = 0, n_col = 0;
         const uint32_t tmem_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-        const int cols = BN >> 1, c_lo = half * cols;   // this thread's columns of every tile
+        const int cols = BN / SEL, c_lo = half * cols;  // this thread's columns of every tile (a multiple of 32)
 
         u64x key[K];                                    // exact (distance, index) list: filled at the end, or earlier on overflow
 #pragma unroll
         for (int j = 0; j < K; ++j) key[j] = kW2Empty;
         int overflow = 0;
+        float* sp = s_stage_v + st;                     // next free staging slot of this thread (index slot: + kW2Stage * kW2Sel)
         auto compact = [&]() {                          // keep the collected pairs at or below the current bound
             int w = 0;
             for (int e = 0; e < n_col; ++e) {
@@ -232,7 +273,8 @@ knn_wide2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             for (int e = 0; e < n_col; ++e) {
                 if (s_col_v[e * kW2Sel + st] > bound) continue;
                 const int m = s_col_i[e * kW2Sel + st];
-                const float d = w2_exact_dist(x, a.s_sc, db + (int64_t)m * a.d_sn, a.d_sc, a.C, qn, a.normalize);
+                const float d = y_vec ? w2_exact_dist_fast(sA, ql, db + (int64_t)m * a.d_sn, a.C, qn, a.normalize)
+                                      : w2_exact_dist(x, a.s_sc, db + (int64_t)m * a.d_sn, a.d_sc, a.C, qn, a.normalize);
                 w2_key_insert<K>(key, ((u64x)w2_dist_bits(d) << 32) | (unsigned)m);
             }
             n_col = 0;
@@ -248,7 +290,7 @@ knn_wide2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             for (int s2 = 0; s2 < most; ++s2) {
                 float v = INFINITY;
                 unsigned short ix = 0;
-                if (s2 < n_st) { v = s_stage_v[s2 * kW2Sel + st]; ix = s_stage_i[s2 * kW2Sel + st]; }
+                if (s2 < n_st) { v = s_stage_v[s2 * kW2Sel + st]; ix = (unsigned short)s_stage_i[s2 * kW2Sel + st]; }
                 if (__any_sync(kFull, v < best[K - 1])) {
                     float w = v;
 #pragma unroll
@@ -257,6 +299,7 @@ knn_wide2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 if (v <= bound) { s_col_v[n_col * kW2Sel + st] = v; s_col_i[n_col * kW2Sel + st] = ix; ++n_col; }
             }
             n_st = 0;
+            sp = s_stage_v + st;
             if (valid) bound = fminf(best[K - 1] + err2, 3.0e38f);
         };
 
@@ -273,15 +316,20 @@ knn_wide2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                     __syncwarp();
                     if (lane == 0) w2_arrive(tempty + s);
                 }
-                const int nvalid = a.M - (m0 + c0);      // columns past M are TMA zero fill: not candidates
+                const int mb = m0 + c0;
+                if (mb + 32 > a.M) {                     // last, ragged tile: columns past M are TMA zero fill, not candidates
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) if (mb + i >= a.M) v[i] = INFINITY;
+                }
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
                         const int i = 8 * g + u;
-                        if (v[i] <= bound && i < nvalid) {
-                            s_stage_v[n_st * kW2Sel + st] = v[i];
-                            s_stage_i[n_st * kW2Sel + st] = (unsigned short)(m0 + c0 + i);
+                        if (v[i] <= bound) {
+                            sp[0] = v[i];
+                            reinterpret_cast<int*>(sp)[kW2Stage * kW2Sel] = mb + i;
+                            sp += kW2Sel;
                             ++n_st;
                         }
                     }
@@ -294,16 +342,20 @@ knn_wide2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         if (overflow && a.stats && lane == 0) atomicAdd(a.stats, 1);
 
         // the second selector of each query hands its exact list to the first one (the staging / collect columns are dead)
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        u64x* s_keys = reinterpret_cast<u64x*>(s_col_v);                    // [K][128] u64: 20 KB <= 48 * 256 * 4
-        if (half == 1) {
+        if constexpr (SEL == 2) {
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            u64x* s_keys = reinterpret_cast<u64x*>(s_col_v);                // [K][128] u64 <= the collect columns
+            if (half == 1) {
 #pragma unroll
-            for (int j = 0; j < K; ++j) s_keys[j * kW2Q + ql] = key[j];
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (valid && half == 0) {
+                for (int j = 0; j < K; ++j) s_keys[j * kW2Q + ql] = key[j];
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (valid && half == 0) {
 #pragma unroll 1
-            for (int j = 0; j < K; ++j) w2_key_insert<K>(key, s_keys[j * kW2Q + ql]);
+                for (int j = 0; j < K; ++j) w2_key_insert<K>(key, s_keys[j * kW2Q + ql]);
+            }
+        }
+        if (valid && half == 0) {
             int64_t* io = a.idx_out + ((int64_t)b * a.N + q) * a.k;
             float* dout = a.dist_out ? a.dist_out + ((int64_t)b * a.N + q) * a.k : nullptr;
 #pragma unroll
@@ -334,8 +386,8 @@ static W2EncodeFn w2_encode_fn() {
     return fn;
 }
 
-static size_t wide2_smem(int KB, int BN) {
-    return (size_t)KB * kW2Q * 128 + 2 * (size_t)KB * BN * 128 + (size_t)(kW2Stage + kW2Cap) * kW2Sel * 6 + 9 * 8 + 16 + 1024;
+static size_t wide2_smem(int KB, int BN, int sel) {
+    return (size_t)KB * kW2Q * 128 + 2 * (size_t)KB * BN * 128 + (size_t)(8 * kW2Stage + 6 * kW2Cap) * 128 * sel + 9 * 8 + 16 + 1024;
 }
 
 }  // namespace ogmm
@@ -352,11 +404,11 @@ int ogmm_launch_knn_wide2(const float* src, int64_t s_sb, int64_t s_sn, int64_t 
     W2EncodeFn encode = w2_encode_fn();
     if (!encode) return OGMM_EUNSUPPORTED;
     const int CA = (int)C + kW2Aug, KB = (CA + 31) / 32;
-    int BN = 64;
+    const int BN = 64;
     const size_t limit = 226 * 1024;
-    while (BN > 32 && wide2_smem(KB, BN) > limit) BN >>= 1;
-    if (wide2_smem(KB, BN) > limit) return OGMM_EUNSUPPORTED;
-    const size_t smem = wide2_smem(KB, BN);
+    const int sel = wide2_smem(KB, BN, 2) <= limit ? 2 : 1;
+    if (wide2_smem(KB, BN, sel) > limit) return OGMM_EUNSUPPORTED;
+    const size_t smem = wide2_smem(KB, BN, sel);
 
     float *aug_q = nullptr, *aug_c = nullptr;
     int* cn_max = nullptr;
@@ -390,18 +442,24 @@ int ogmm_launch_knn_wide2(const float* src, int64_t s_sb, int64_t s_sn, int64_t 
     }
     Wide2Args a{src, s_sb, s_sn, s_sc, dst, d_sb, d_sn, d_sc, (int)N, (int)M, (int)C, (int)k, normalize, BN, KB, cn_max, idx_out, dist_out, stats};
     dim3 grid((unsigned)((N + kW2Q - 1) / kW2Q), (unsigned)B);
-#define LAUNCH(KK)                                                                                                   \
+#define LAUNCH2(KK, SS)                                                                                              \
     do {                                                                                                             \
-        st = cuda_status(cudaFuncSetAttribute(knn_wide2_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+        st = cuda_status(cudaFuncSetAttribute(knn_wide2_kernel<KK, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                               (int)smem), "cudaFuncSetAttribute(knn_wide2_kernel)");                 \
         if (st != OGMM_OK) return fail(st);                                                                          \
-        knn_wide2_kernel<KK><<<grid, kW2Threads, smem, s>>>(map_q, map_c, a);                                        \
+        knn_wide2_kernel<KK, SS><<<grid, 128 + 128 * SS, smem, s>>>(map_q, map_c, a);                                \
+    } while (0)
+#define LAUNCH(KK)                                                                                                   \
+    do {                                                                                                             \
+        if (sel == 2) LAUNCH2(KK, 2);                                                                                \
+        else LAUNCH2(KK, 1);                                                                                         \
     } while (0)
     if (k <= 8) LAUNCH(8);
     else if (k <= 16) LAUNCH(16);
     else if (k <= 20) LAUNCH(20);
     else LAUNCH(32);
 #undef LAUNCH
+#undef LAUNCH2
     st = cuda_status(cudaGetLastError(), "knn_wide2_kernel");
     cudaFreeAsync(aug_q, s);
     return st;

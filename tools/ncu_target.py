@@ -25,3 +25,9 @@ for _ in range(reps):
         from ogmm_b200 import pipeline
         pipeline.register_hot_path(d["src"], d["tgt"], d["src_feats"], d["tgt_feats"], d["src_o"], d["tgt_o"], 16, 20, overlap=False)
 torch.cuda.synchronize()
+if what == "wide":
+    g = torch.Generator().manual_seed(64)
+    xw = torch.relu(torch.randn(1, 16384, 64, generator=g)).cuda()
+    for _ in range(reps):
+        ops.knn_graph(xw, xw, 20)
+    torch.cuda.synchronize()
