@@ -120,7 +120,7 @@ template <int K>
 __global__ void __launch_bounds__(kSwThreads, 2)
 knn3_select_kernel(const float* __restrict__ src, int64_t s_sb, int64_t s_sn, int64_t s_sc,
                    const float* __restrict__ dst, int64_t d_sb, int64_t d_sn, int64_t d_sc,
-                   int B, int N, int M, int k, int self,
+                   int B, int N, int M, int k, int self, int items_per_cta,
                    int64_t* __restrict__ idx_out, float* __restrict__ dist_out, float* __restrict__ edge_out,
                    int32_t* __restrict__ stats) {
     extern __shared__ __align__(16) unsigned char sel_raw[];
@@ -138,8 +138,11 @@ knn3_select_kernel(const float* __restrict__ src, int64_t s_sb, int64_t s_sn, in
     const unsigned gmask = NG <= 256 ? 0xffu : 0x3ffu;                          // M <= 4096 -> NG <= 1024
     const int blocks_per_cloud = (N + kSwQueriesPerCta - 1) / kSwQueriesPerCta;
     const int64_t items = (int64_t)B * blocks_per_cloud;
-    // contiguous item range per CTA: consecutive items share a cloud, so the cloud is staged and sorted once for them
-    const int64_t it_begin = items * blockIdx.x / gridDim.x, it_end = items * (blockIdx.x + 1) / gridDim.x;
+    // contiguous item range per CTA: consecutive items share a cloud, so the cloud is staged and sorted once for them.
+    // items_per_cta > 0: fixed-size ranges that start on cloud boundaries (or divide a cloud evenly), chosen by the host
+    // when that costs no extra round; otherwise the items are split proportionally over the grid.
+    const int64_t it_begin = items_per_cta > 0 ? (int64_t)blockIdx.x * items_per_cta : items * blockIdx.x / gridDim.x;
+    const int64_t it_end = items_per_cta > 0 ? min(items, it_begin + items_per_cta) : items * (blockIdx.x + 1) / gridDim.x;
     int staged = -1;
     float cn_max = 0.f;
     int axis = 0;
@@ -438,7 +441,7 @@ int ogmm_launch_knn3_select(const float* src, int64_t s_sb, int64_t s_sn, int64_
     if (st != OGMM_OK) return st;
     st = cuda_status(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "cudaDeviceGetAttribute");
     if (st != OGMM_OK) return st;
-    const int64_t items = B * ((N + kSwQueriesPerCta - 1) / kSwQueriesPerCta);
+    const int64_t blocks = (N + kSwQueriesPerCta - 1) / kSwQueriesPerCta, items = B * blocks;
 #define LAUNCH(KK)                                                                                                  \
     do {                                                                                                            \
         st = cuda_status(cudaFuncSetAttribute(knn3_select_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
@@ -449,11 +452,16 @@ int ogmm_launch_knn3_select(const float* src, int64_t s_sb, int64_t s_sn, int64_
                                                                        smem), "cudaOccupancyMaxActiveBlocksPerMultiprocessor"); \
         if (st != OGMM_OK) return st;                                                                               \
         if (per_sm < 1) per_sm = 1;                                                                                 \
-        const int64_t grid = items < (int64_t)sms * per_sm ? items : (int64_t)sms * per_sm;                         \
+        int64_t grid = items < (int64_t)sms * per_sm ? items : (int64_t)sms * per_sm;                               \
+        /* rounds every CTA needs anyway; if whole clouds (or even fractions of one) fit that count, give every CTA \
+           such a range: each cloud is then sorted once per CTA that owns part of it instead of ~2.2 times */       \
+        const int64_t per = (items + grid - 1) / grid;                                                              \
+        int items_per_cta = 0;                                                                                      \
+        if (per % blocks == 0 || blocks % per == 0) { items_per_cta = (int)per; grid = (items + per - 1) / per; }   \
         knn3_select_kernel<KK><<<(unsigned)grid, kSwThreads, smem, s>>>(src, s_sb, s_sn, s_sc, dst, d_sb, d_sn,     \
                                                                         d_sc, (int)B, (int)N, (int)M, (int)k,       \
-                                                                        self ? 1 : 0, idx_out, dist_out, edge_out,  \
-                                                                        stats);                                     \
+                                                                        self ? 1 : 0, items_per_cta, idx_out,       \
+                                                                        dist_out, edge_out, stats);                 \
     } while (0)
     if (k <= 4) LAUNCH(4);
     else if (k <= 8) LAUNCH(8);
