@@ -773,6 +773,24 @@ def test_register_from_host_matches_device_path(og):
     assert h2d == sum(v.numel() * 4 for v in pinned.values()) and d2h == 24 * 12 * 4
 
 
+def test_host_boundary_matches_register_from_host(og):
+    """pipeline.HostBoundary (xyz + overlap scores from pinned host memory, features resident, one graph launch per step)
+    returns exactly what the eager host-buffer entry point returns, also for new inputs written into the same buffers."""
+    from ogmm_b200 import pipeline, synth
+    keys = ("src", "tgt", "src_feats", "tgt_feats", "src_o", "tgt_o")
+    batches = []
+    for first in (0, 11):
+        h = synth.hot_path_inputs(first, 16, 1024, 128)
+        batches.append({k: torch.from_numpy(np.ascontiguousarray(h[k])).float().pin_memory() for k in keys})
+    dev = torch.device("cuda:0")
+    fs, ft = batches[0]["src_feats"].cuda(), batches[0]["tgt_feats"].cuda()
+    hb = pipeline.HostBoundary(batches[0], dev, fs, ft, 16, 20)
+    for b in batches:
+        rot, trans, h2d, d2h = hb(b)
+        ref_rot, ref_trans, h2d_ref, _ = pipeline.register_from_host(b, dev, 16, 20, device_feats=(fs, ft))
+        assert torch.equal(rot, ref_rot) and torch.equal(trans, ref_trans) and h2d == h2d_ref == 16 * 1024 * 4 * 8
+
+
 def test_graphed_hot_path_replays_the_eager_result(og):
     """The CUDA-graph replay of a step (static inputs) is bit-identical to the eager call, also after the inputs
     were overwritten in place."""
