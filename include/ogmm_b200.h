@@ -219,6 +219,25 @@ int ogmm_soft_procrustes(const float* src_mu, const float* tgt_mu, const float* 
                          float* rot_out, float* trans_out, float* corr_out, float* sim_out,
                          ogmm_stream_t stream);
 
+/* Backward of the two heads above -- what the reference gets from autograd through torch.svd when train.py:69-75
+ * back-propagates the registration loss on (R, t).  Closed-form chain rule in one launch (fp64 3x3 algebra); forward
+ * quantities are recomputed from the inputs, so the forward saves nothing.  grad_rot (B,3,3), grad_trans (B,3) and
+ * grad_corr (B,3,Js) are the upstream gradients; each may be NULL (= zero).
+ *   ogmm_rigid_transform_backward: inputs as ogmm_rigid_transform; grad_src, grad_corr (B,3,n), grad_weight (B,1,n)
+ *   contiguous outputs.
+ *   ogmm_soft_procrustes_backward: inputs as ogmm_soft_procrustes; grad_src_mu (B,Js,3), grad_tgt_mu (B,Jt,3),
+ *   grad_src_desc (B,Js,D), grad_tgt_desc (B,Jt,D) contiguous outputs. */
+int ogmm_rigid_transform_backward(const float* src, int64_t s_sb, int64_t s_sc, int64_t s_sn,
+                                  const float* corr, int64_t c_sb, int64_t c_sc, int64_t c_sn,
+                                  const float* weight, int64_t w_sb, int64_t w_sn, int64_t B, int64_t n,
+                                  const float* grad_rot, const float* grad_trans,
+                                  float* grad_src, float* grad_corr, float* grad_weight, ogmm_stream_t stream);
+int ogmm_soft_procrustes_backward(const float* src_mu, const float* tgt_mu, const float* src_desc,
+                                  const float* tgt_desc, int64_t B, int64_t Js, int64_t Jt, int64_t D,
+                                  float temperature, const float* grad_rot, const float* grad_trans,
+                                  const float* grad_corr, float* grad_src_mu, float* grad_tgt_mu,
+                                  float* grad_src_desc, float* grad_tgt_desc, ogmm_stream_t stream);
+
 /* Cosine similarity alone (lib/utils.py:222-226): x (B,N,D), y (B,M,D) contiguous -> (B,N,M).
  * Sized for component descriptors (the GMMSVD head, N = Js, M = Jt): one CTA holds the N x M similarity tile in
  * shared memory, so N * M is limited to about 45,000 entries (e.g. 200 x 200); larger calls return

@@ -50,6 +50,10 @@ SIGNATURES = {
     "ogmm_softmax_moments": (i32, [c_f, c_f, i64, i64, i64, i64, i64, i64, c_f, c_f, c_f, c_f, vp]),
     "ogmm_rigid_transform": (i32, [c_f, i64, i64, i64, c_f, i64, i64, i64, c_f, i64, i64, i64, i64, c_f, c_f, vp]),
     "ogmm_soft_procrustes": (i32, [c_f, c_f, c_f, c_f, i64, i64, i64, i64, f32, c_f, c_f, c_f, c_f, vp]),
+    "ogmm_rigid_transform_backward": (i32, [c_f, i64, i64, i64, c_f, i64, i64, i64, c_f, i64, i64, i64, i64, c_f, c_f,
+                                            c_f, c_f, c_f, vp]),
+    "ogmm_soft_procrustes_backward": (i32, [c_f, c_f, c_f, c_f, i64, i64, i64, i64, f32, c_f, c_f, c_f, c_f, c_f, c_f,
+                                            c_f, vp]),
     "ogmm_cos_similarity": (i32, [c_f, c_f, i64, i64, i64, i64, c_f, vp]),
     "ogmm_gmm_register": (i32, [c_f, c_f, c_f, c_f, i64, i64, c_f, vp]),
 }

@@ -1,5 +1,6 @@
-"""Backward support for the differentiable piece of the path that the reference trains through first (SURVEY.md
-section 8(f) N4): the feature M-step ``node_feats = gmm_params(gamma, feats)[1]`` (lib/utils.py:289).
+"""Backward support for the differentiable pieces of the path the reference trains through (SURVEY.md section 8(f)
+N4): the feature M-step ``node_feats = gmm_params(gamma, feats)[1]`` (lib/utils.py:289), the soft-correspondence head
+``GMMSVD(is_sk=False)`` (models/dgcnn.py:96-115) and ``compute_rigid_transformation`` (lib/se3.py:256-289).
 
 In the reference's training step (train.py:57-75) the Sinkhorn loop runs under ``no_grad`` and ``gamma`` is detached
 (lib/utils.py:275-286), so autograd enters the clustering only through ``feats``:
@@ -43,3 +44,47 @@ def can_differentiate(gamma, pts, return_sigma=False):
 def feature_moments(gamma, feats):
     """(pi, mu) with autograd history into ``feats``."""
     return FeatureMoments.apply(gamma.detach(), feats)
+
+
+class SoftProcrustes(torch.autograd.Function):
+    """GMMSVD(is_sk=False) -> (R, t, corr).  Backward = ``ogmm_soft_procrustes_backward`` (closed-form chain through the
+    softmax correspondences, the weighted covariance and the 3x3 SVD); inputs are saved, nothing else."""
+
+    @staticmethod
+    def forward(ctx, src_mu, tgt_mu, src_desc, tgt_desc, temperature):
+        rot, t, corr, _ = ops.soft_procrustes(src_mu, tgt_mu, src_desc, tgt_desc, temperature=temperature)
+        ctx.save_for_backward(src_mu, tgt_mu, src_desc, tgt_desc)
+        ctx.temperature = temperature
+        return rot, t, corr
+
+    @staticmethod
+    def backward(ctx, grad_rot, grad_t, grad_corr):
+        src_mu, tgt_mu, src_desc, tgt_desc = ctx.saved_tensors
+        g = ops.soft_procrustes_backward(src_mu, tgt_mu, src_desc, tgt_desc, _f32(grad_rot), _f32(grad_t), _f32(grad_corr),
+                                         temperature=ctx.temperature)
+        return tuple(gi if need else None for gi, need in zip(g, ctx.needs_input_grad[:4])) + (None,)
+
+
+class RigidTransform(torch.autograd.Function):
+    """compute_rigid_transformation -> (R (B,3,3), t (B,3)).  Backward = ``ogmm_rigid_transform_backward``."""
+
+    @staticmethod
+    def forward(ctx, src, corr, weight):
+        rot, t = ops.rigid_transform(src, corr, weight)
+        ctx.save_for_backward(src, corr, weight)
+        return rot, t
+
+    @staticmethod
+    def backward(ctx, grad_rot, grad_t):
+        src, corr, weight = ctx.saved_tensors
+        g = ops.rigid_transform_backward(src, corr, weight, _f32(grad_rot), _f32(grad_t))
+        return tuple(gi if need else None for gi, need in zip(g, ctx.needs_input_grad))
+
+
+def _f32(g):
+    return None if g is None else g.float()
+
+
+def records(*tensors):
+    """True when autograd would have to record a call on these tensors."""
+    return torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors)

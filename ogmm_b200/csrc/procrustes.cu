@@ -109,7 +109,7 @@ constexpr int kSPThreads = 256;
 constexpr int kPairsPerThread = 16;
 
 __host__ __device__ inline size_t soft_procrustes_smem(int Js, int Jt) {
-    return sizeof(float) * ((size_t)Js * Jt + (size_t)(Js + Jt) * kDTP + (Js + Jt) + 3 * (size_t)Js + Js + 3 * (size_t)(Js + Jt) + 32);
+    return sizeof(float) * ((((size_t)Js * Jt + 3) & ~(size_t)3) + (size_t)(Js + Jt) * kDTP + (Js + Jt) + 3 * (size_t)Js + Js + 3 * (size_t)(Js + Jt) + 32);
 }
 
 // Steps 3-5 of GMMSVD shared by both similarity kernels: softmax(sim / T) rows, soft correspondences, weights,
@@ -180,7 +180,7 @@ soft_procrustes_kernel(const float* __restrict__ src_mu, const float* __restrict
                        float* __restrict__ corr_out, float* __restrict__ sim_out, int head) {
     extern __shared__ __align__(16) float smem[];
     float* sim = smem;
-    float* xs = sim + (size_t)Js * Jt;
+    float* xs = sim + (((size_t)Js * Jt + 3) & ~(size_t)3);      // the descriptor tiles are read as float4: 16-byte aligned
     float* yt = xs + (size_t)Js * kDTP;
     float* den = yt + (size_t)Jt * kDTP;
     float* corr = den + (Js + Jt);

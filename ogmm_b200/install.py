@@ -16,9 +16,10 @@ Two things to know:
   autograd is recording and an argument requires grad (``train.py:57-75``: the loss calls ``gmm_params``,
   ``get_local_corrs``; the model differentiates through ``gmm_params(gamma, feats)``, ``GMMSVD`` and
   ``compute_rigid_transformation``) the call goes to the reference's own function that the name held before -- exactly
-  what would have run without ``install()``.  Replacements that carry their own backward (``wkeans_plus`` and
-  ``gmm_params`` on wide features: the feature M-step, see ``ogmm_b200/autograd.py``) take those calls themselves.  Under ``torch.no_grad()`` / inference every
-  call runs on the kernels.
+  what would have run without ``install()``.  Replacements that carry their own backward (``ogmm_b200/autograd.py``:
+  ``wkeans_plus`` and ``gmm_params`` on wide features = the feature M-step, ``GMMSVD(is_sk=False)`` = the
+  soft-correspondence head, ``compute_rigid_transformation``) take those calls themselves.  Under ``torch.no_grad()`` /
+  inference every call runs on the kernels.
 * **Classes.**  ``models.gmmreg.Clustering`` and ``GMMSVD`` are replaced by subclasses of ``ogmm_b200.modules`` that
   dispatch the same way; they take effect for models constructed AFTER ``install()``.  A model built earlier still
   benefits (its modules call the patched function names), and ``install(model=net)`` additionally switches the class
@@ -86,7 +87,8 @@ def _class_dispatcher(ours_cls, ref_cls):
         __doc__ = ours_cls.__doc__
 
         def forward(self, *args, **kwargs):
-            if _needs_grad(args, kwargs):
+            can = getattr(ours_cls, "ogmm_can_differentiate", None)   # classes with a backward of their own say when
+            if _needs_grad(args, kwargs) and not (can is not None and can(self, *args, **kwargs)):
                 return ref_cls.forward(self, *args, **kwargs)        # same attributes (is_sk / n_clusters): duck-typed self
             return ours_cls.forward(self, *args, **kwargs)
 

@@ -11,7 +11,7 @@ from __future__ import annotations
 import torch
 from torch import nn
 
-from . import ops
+from . import autograd, ops
 from ._guard import forward_only
 from .se3 import compute_rigid_transformation
 from .utils import wkeans_plus
@@ -30,6 +30,9 @@ class Clustering(nn.Module):
         return wkeans_plus(xyz.transpose(-1, -2), feats.transpose(-1, -2), o_scores, self.n_clusters,
                            iters=10, tau=1.0)
 
+    def ogmm_can_differentiate(self, *args, **kwargs):
+        return True                      # wkeans_plus: clustering under no_grad, differentiable feature M-step
+
 
 class GMMSVD(nn.Module):
     """models/dgcnn.py:90-115.  ``is_sk=False`` (how models/gmmreg.py:41 builds it) is one fused kernel."""
@@ -39,12 +42,23 @@ class GMMSVD(nn.Module):
         self.is_sk = is_sk
         self.epsilon = epsilon
 
-    @forward_only
     def forward(self, src, tgt, src_desc, tgt_desc, src_pi, tgt_pi):
         batch_size = src.size(0)
         if not self.is_sk:
-            R, t, src_corr, _ = ops.soft_procrustes(src, tgt, src_desc, tgt_desc, temperature=0.05)
+            if autograd.records(src, tgt, src_desc, tgt_desc):            # training: the head brings its own backward
+                R, t, src_corr = autograd.SoftProcrustes.apply(src, tgt, src_desc, tgt_desc, 0.05)
+            else:
+                with torch.no_grad():
+                    R, t, src_corr, _ = ops.soft_procrustes(src, tgt, src_desc, tgt_desc, temperature=0.05)
             return R, t.view(batch_size, 3), src_corr, tgt.transpose(-1, -2)
+        return self._forward_sk(src, tgt, src_desc, tgt_desc, src_pi, tgt_pi)
+
+    def ogmm_can_differentiate(self, *args, **kwargs):
+        return not self.is_sk            # the softmax head has a backward kernel; the Sinkhorn variant does not
+
+    @forward_only
+    def _forward_sk(self, src, tgt, src_desc, tgt_desc, src_pi, tgt_pi):
+        batch_size = src.size(0)
         similarity = ops.cos_similarity(src_desc, tgt_desc)
         scores = ops.sinkhorn(2.0 * (1.0 - similarity), src_pi, tgt_pi, 1e-2, 1e-2, 30)[0]
         scores = torch.nan_to_num(scores, 1e-4)

@@ -288,6 +288,61 @@ def soft_procrustes(src_mu, tgt_mu, src_desc, tgt_desc, temperature=0.05, want_s
     return rot, t, corr, sim
 
 
+def rigid_transform_backward(src, corr, weight, grad_rot, grad_trans):
+    """Gradients of ``rigid_transform``: src, corr (B,3,n) views, weight (B,1,n) view, grad_rot (B,3,3) | None,
+    grad_trans (B,3) | None -> grad_src (B,3,n), grad_corr (B,3,n), grad_weight (B,1,n)."""
+    _need_cuda_f32("src", src); _need_cuda_f32("corr", corr); _need_cuda_f32("weight", weight)
+    B, three, n = src.shape
+    if three != 3 or tuple(corr.shape) != (B, 3, n) or tuple(weight.shape) != (B, 1, n):
+        raise ValueError("rigid_transform_backward: expected src/corr (B,3,n) and weight (B,1,n)")
+    dev = src.device
+    if grad_rot is not None:
+        _need_cuda_f32("grad_rot", grad_rot)
+        grad_rot = grad_rot.reshape(B, 3, 3).contiguous()
+    if grad_trans is not None:
+        _need_cuda_f32("grad_trans", grad_trans)
+        grad_trans = grad_trans.reshape(B, 3).contiguous()
+    g_src = torch.empty((B, 3, n), dtype=torch.float32, device=dev)
+    g_corr = torch.empty((B, 3, n), dtype=torch.float32, device=dev)
+    g_w = torch.empty((B, 1, n), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        st = _lib.load().ogmm_rigid_transform_backward(src.data_ptr(), *src.stride(), corr.data_ptr(), *corr.stride(),
+                                                       weight.data_ptr(), weight.stride(0), weight.stride(2), B, n,
+                                                       _ptr(grad_rot), _ptr(grad_trans), g_src.data_ptr(),
+                                                       g_corr.data_ptr(), g_w.data_ptr(), _stream(src))
+    _lib.check(st, "ogmm_rigid_transform_backward")
+    return g_src, g_corr, g_w
+
+
+def soft_procrustes_backward(src_mu, tgt_mu, src_desc, tgt_desc, grad_rot, grad_trans, grad_corr, temperature=0.05):
+    """Gradients of ``soft_procrustes`` given dL/dR (B,3,3) | None, dL/dt (B,3) | None, dL/dcorr (B,3,Js) | None ->
+    grad_src_mu (B,Js,3), grad_tgt_mu (B,Jt,3), grad_src_desc (B,Js,D), grad_tgt_desc (B,Jt,D)."""
+    for n_, t_ in (("src_mu", src_mu), ("tgt_mu", tgt_mu), ("src_desc", src_desc), ("tgt_desc", tgt_desc)):
+        _need_cuda_f32(n_, t_)
+    B, Js, _ = src_mu.shape
+    Jt = tgt_mu.shape[1]
+    D = src_desc.shape[2]
+    if tuple(src_desc.shape) != (B, Js, D) or tuple(tgt_desc.shape) != (B, Jt, D) or tgt_mu.shape[2] != 3 or src_mu.shape[2] != 3:
+        raise ValueError("soft_procrustes_backward: inconsistent shapes")
+    src_mu, tgt_mu, src_desc, tgt_desc = (t_.contiguous() for t_ in (src_mu, tgt_mu, src_desc, tgt_desc))
+    grads = []
+    for n_, g, shape in (("grad_rot", grad_rot, (B, 3, 3)), ("grad_trans", grad_trans, (B, 3)), ("grad_corr", grad_corr, (B, 3, Js))):
+        if g is not None:
+            _need_cuda_f32(n_, g)
+            g = g.reshape(shape).contiguous()
+        grads.append(g)
+    dev = src_mu.device
+    g_smu, g_tmu = torch.empty_like(src_mu), torch.empty_like(tgt_mu)
+    g_sd, g_td = torch.empty_like(src_desc), torch.empty_like(tgt_desc)
+    with torch.cuda.device(dev):
+        st = _lib.load().ogmm_soft_procrustes_backward(src_mu.data_ptr(), tgt_mu.data_ptr(), src_desc.data_ptr(),
+                                                       tgt_desc.data_ptr(), B, Js, Jt, D, float(temperature),
+                                                       _ptr(grads[0]), _ptr(grads[1]), _ptr(grads[2]), g_smu.data_ptr(),
+                                                       g_tmu.data_ptr(), g_sd.data_ptr(), g_td.data_ptr(), _stream(src_mu))
+    _lib.check(st, "ogmm_soft_procrustes_backward")
+    return g_smu, g_tmu, g_sd, g_td
+
+
 def cos_similarity(x, y):
     """x (B,N,D), y (B,M,D) -> (B,N,M) cosine similarity."""
     _need_cuda_f32("x", x); _need_cuda_f32("y", y)

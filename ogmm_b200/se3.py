@@ -7,8 +7,7 @@ from __future__ import annotations
 
 import torch
 
-from . import ops
-from ._guard import forward_only
+from . import autograd, ops
 
 __all__ = ["decompose_trans", "integrate_trans", "torch_identity", "torch_inverse", "torch_concatenate",
            "torch_transform", "compute_rigid_transformation"]
@@ -65,8 +64,15 @@ def torch_transform(g, a, normals=None):
     return b
 
 
-@forward_only
 def compute_rigid_transformation(src, src_corr, weight):
-    """lib/se3.py:256-289.  src, src_corr (B,3,n), weight (B,1,n) -> R (B,3,3), t (B,3,1)."""
-    rot, t = ops.rigid_transform(src, src_corr, weight)
+    """lib/se3.py:256-289.  src, src_corr (B,3,n), weight (B,1,n) -> R (B,3,3), t (B,3,1).  Differentiable: when autograd
+    records the call the backward kernel (``ogmm_rigid_transform_backward``) supplies the gradients."""
+    if autograd.records(src, src_corr, weight):
+        rot, t = autograd.RigidTransform.apply(src, src_corr, weight)
+    else:
+        with torch.no_grad():
+            rot, t = ops.rigid_transform(src, src_corr, weight)
     return rot, t.unsqueeze(-1)
+
+
+compute_rigid_transformation.ogmm_autograd_safe = True

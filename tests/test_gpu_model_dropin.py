@@ -167,3 +167,51 @@ def test_deepgmr_forward_patched_equals_unpatched(ref):
     # the E+M stage feeding it, on the model's own logits: compare the GMM parameters the two runs produced
     assert e_rot <= max(0.1, 20 * spread)
     assert torch.equal(bot1, bot0), "the caller returns T[:, 3, :3] (zeros) as 'translation' (baseline/deepgmr.py:79)"
+
+
+def test_gmmreg_training_step_patched_equals_unpatched(ref):
+    """One training step of the unmodified GMMReg (train.py:53-75: forward in train() mode, the registration + clustering +
+    overlap loss, backward) before and after install().  With install() active the differentiable pieces run on OUR
+    forward and backward kernels -- the feature M-step inside wkeans_plus (FeatureMoments) and the soft-correspondence
+    head (SoftProcrustes) -- and every parameter gradient must agree with the reference's own autograd."""
+    from oracle import refload
+    import ogmm_b200.install as inst
+    torch.manual_seed(99)
+    model = ref["gmmreg"].GMMReg(512, 16, refload.model_config()).cuda().train()
+    from ogmm_b200 import synth
+    s, t, R_gt, t_gt = synth.modelnet_batch(3, 4, 1024)
+    src, tgt = torch.from_numpy(s).cuda(), torch.from_numpy(t).cuda()
+    rot_gt, trans_gt = torch.from_numpy(R_gt).cuda().float(), torch.from_numpy(t_gt).cuda().float().view(4, 3)
+    o_gt = (torch.rand(4, 2048, generator=torch.Generator().manual_seed(1)) > 0.4).float().cuda()
+    loss_mod = ref["loss"]
+
+    def step(seed):
+        model.zero_grad(set_to_none=True)
+        torch.manual_seed(seed)
+        with torch.backends.cudnn.flags(enabled=False):
+            rot, trans, src_o, tgt_o, clu_loss = model(src, tgt)
+            o_pred = torch.nan_to_num(torch.cat([src_o, tgt_o], dim=-1), nan=0.0).clip(min=0.0)
+            loss = 10 * loss_mod.dcp_loss(rot, rot_gt, trans, trans_gt) + clu_loss + loss_mod.get_weighted_bce_loss(o_pred, o_gt)
+            loss.backward()
+        torch.cuda.synchronize()
+        grads = {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
+        return rot, float(loss), grads
+
+    rot0, loss0, g0 = step(7)
+    _, loss0b, g0b = step(7)
+    noise = max(float((g0[n] - g0b[n]).norm() / g0[n].norm().clamp(min=1e-20)) for n in g0)     # atomics in the reference's own backward
+    inst.install(model=model)
+    try:
+        rot1, loss1, g1 = step(7)
+    finally:
+        inst.uninstall()
+    assert "SoftProcrustes" in type(rot1.grad_fn).__name__, f"the head's backward kernel must be on the graph, got {rot1.grad_fn}"
+    assert set(g1) == set(g0) and len(g0) > 20
+    num = sum(float((g1[n].double() - g0[n].double()).pow(2).sum()) for n in g0) ** 0.5
+    den = sum(float(g0[n].double().pow(2).sum()) for n in g0) ** 0.5
+    worst = max(((float((g1[n] - g0[n]).norm() / g0[n].norm().clamp(min=1e-20)), n) for n in g0 if float(g0[n].norm()) > 1e-6 * den))
+    print(f"\n  GMMReg training step patched vs unpatched (B=4): loss {loss0:.6f} vs {loss1:.6f}; all-parameter gradient "
+          f"relative error {num / den:.2e}; worst tensor {worst[1]} {worst[0]:.2e}; reference run-to-run noise {noise:.2e}; "
+          f"{len(g0)} parameter tensors")
+    assert abs(loss1 - loss0) <= 1e-3 * max(abs(loss0), 1e-6)
+    assert num / den < 2e-2 and worst[0] < 5e-2

@@ -48,10 +48,16 @@ def test_install_rebinds_every_import_site_and_uninstall_restores():
         with pytest.raises(TypeError, match="CUDA"):
             lib.loss.gmm_params(g, torch.rand(2, 32, 8, requires_grad=True))
         f = torch.rand(2, 32, 8)
-        head = models.gmmreg.GMMSVD(False)
+        # the softmax head (how models/gmmreg.py:41 builds it) has a backward kernel too; the Sinkhorn head does not and
+        # stays with the reference's forward when autograd records
         d = torch.rand(2, 4, 8, requires_grad=True)
-        rot = head(torch.rand(2, 4, 3), torch.rand(2, 4, 3), d, torch.rand(2, 4, 8), None, None)[0]
-        assert rot.grad_fn is not None
+        with pytest.raises(TypeError, match="CUDA"):
+            models.gmmreg.GMMSVD(False)(torch.rand(2, 4, 3), torch.rand(2, 4, 3), d, torch.rand(2, 4, 8), None, None)
+        pi4 = torch.full((2, 4), 0.25)
+        # Sinkhorn head under autograd: the reference's forward runs (its own sinkhorn on the graph) up to the Procrustes
+        # solve, which is differentiable here and therefore a kernel call
+        with pytest.raises(TypeError, match="weight|src|corr"):
+            models.gmmreg.GMMSVD(True)(torch.rand(2, 4, 3), torch.rand(2, 4, 3), d, torch.rand(2, 4, 8), pi4, pi4)
         # ... and without a graph the same name reaches the kernels (here: their CUDA-only check)
         with torch.no_grad():
             with pytest.raises(TypeError, match="CUDA"):
@@ -86,11 +92,15 @@ def test_forward_only_guard_is_loud():
         utils.gmm_params(g.detach(), x.clone().requires_grad_(), True)               # sigma
     with pytest.raises(TypeError, match="CUDA"):                       # the feature M-step IS differentiable: reaches the kernels
         utils.gmm_params(g.detach(), x.clone().requires_grad_())
-    with pytest.raises(RuntimeError, match="forward-only"):
+    # the Procrustes solve and the softmax head are differentiable (backward kernels): such calls reach the kernels
+    with pytest.raises(TypeError, match="CUDA"):
         se3.compute_rigid_transformation(torch.rand(2, 3, 8, requires_grad=True), torch.rand(2, 3, 8), torch.rand(2, 1, 8))
-    with pytest.raises(RuntimeError, match="forward-only"):
+    with pytest.raises(TypeError, match="CUDA"):
         modules.GMMSVD(is_sk=False)(torch.rand(2, 4, 3), torch.rand(2, 4, 3), torch.rand(2, 4, 8, requires_grad=True),
                                     torch.rand(2, 4, 8), torch.rand(2, 4), torch.rand(2, 4))
+    with pytest.raises(RuntimeError, match="forward-only"):            # the Sinkhorn head has no backward
+        modules.GMMSVD(is_sk=True)(torch.rand(2, 4, 3), torch.rand(2, 4, 3), torch.rand(2, 4, 8, requires_grad=True),
+                                   torch.rand(2, 4, 8), torch.rand(2, 4), torch.rand(2, 4))
     # without a graph to record, the same call goes on to the kernels (and, on this CPU box, to the CUDA-only check)
     with torch.no_grad():
         with pytest.raises(TypeError, match="CUDA"):
