@@ -110,6 +110,18 @@ int ogmm_edge_conv_max(const float* x, int64_t x_sb, int64_t x_sc, int64_t x_sn,
                        int64_t B, int64_t N, int64_t k, int64_t C,
                        float* act_out, float* max_out, ogmm_stream_t stream);
 
+/* N3, second half: the k = 5 angle feature of PositionEncoding.forward (models/attn.py:65-73) fused with conv_ang1
+ * (Conv2d(1 -> C, bias=False) + BatchNorm2d in eval mode + LeakyReLU(slope)) and the max over the k neighbours:
+ *   alpha[b,n,kk] = < normalize(x_j - x_i), normalize(x_i - centroid_b) >,   j = idx[b,n,kk]  (F.normalize, eps 1e-12)
+ *   max_out[b,c,n] = max_kk leaky((weight[c] * alpha) * scale[c] + shift[c])
+ * x (B,3,N) strided (b,c,n); centroid (B,3) = mean over the points (the caller's torch.mean); idx (B,N,k) int64;
+ * weight, scale, shift (C) with BatchNorm folded as in ogmm_edge_conv_max; alpha_out (B,N,k) optional (NULL to skip);
+ * max_out (B,C,N).  slope >= 0. */
+int ogmm_edge_angle_max(const float* x, int64_t x_sb, int64_t x_sc, int64_t x_sn, const float* centroid,
+                        const int64_t* idx, const float* weight, const float* scale, const float* shift, float slope,
+                        int64_t B, int64_t N, int64_t k, int64_t C, float* alpha_out, float* max_out,
+                        ogmm_stream_t stream);
+
 /* ---- farthest point sampling -----------------------------------------------------------------
  * Replaces lib/utils.py:170-198 farthest_point_sample.  xyz (B,N,3) strided view.
  *   start == NULL: is_center=True (start from the point farthest from the centroid);

@@ -36,6 +36,7 @@ SIGNATURES = {
     "ogmm_knn_wide": (i32, [c_f, i64, i64, i64, c_f, i64, i64, i64, i64, i64, i64, i64, i64, i32, c_i64p, c_f, c_i32p, vp]),
     "ogmm_edge_gather": (i32, [c_f, i64, i64, i64, c_i64p, i64, i64, i64, i64, c_f, vp]),
     "ogmm_edge_conv_max": (i32, [c_f, i64, i64, i64, c_i64p, c_f, c_f, c_f, i64, i64, i64, i64, c_f, c_f, vp]),
+    "ogmm_edge_angle_max": (i32, [c_f, i64, i64, i64, c_f, c_i64p, c_f, c_f, c_f, f32, i64, i64, i64, i64, c_f, c_f, vp]),
     "ogmm_fps": (i32, [c_f, i64, i64, i64, i64, i64, i64, c_i64p, c_i64p, c_f, vp]),
     "ogmm_sinkhorn_cluster_workspace": (i64, [i64, i64, i64, i64, i64]),
     "ogmm_sinkhorn_cluster": (i32, [c_f, i64, i64, i64, c_f, i64, i64, i64, i64, f32, f32, f32, i64,

@@ -110,6 +110,69 @@ edge_conv_max_kernel(const float* __restrict__ x, int64_t x_sb, int64_t x_sc, in
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// N3, second half: the k = 5 angle feature of PositionEncoding.forward (models/attn.py:65-73) in one launch:
+//
+//     p2gc  = points - mean_n(points)                                   (B,3,N)
+//     p2lc  = get_graph_feature(points, k)[:, :3]                       (B,3,N,k)    x_j - x_i
+//     alpha = <normalize(p2lc, dim=1), normalize(p2gc, dim=1)>          (B,1,N,k)    F.normalize: v / max(|v|, 1e-12)
+//     out   = conv_ang1(alpha).max(dim=-1)[0]                           (B,C,N)      Conv2d(1 -> C, bias=False) + BN (eval) + LeakyReLU
+//
+// Neither the (B,6,N,k) edge tensor nor the (B,C,N,k) activation is materialised.  Per channel the map
+// alpha -> leaky(fma(w_c * alpha, scale_c, shift_c)) is monotone (rounded products and sums are monotone), so the max
+// over the k neighbours is that map applied to the largest alpha (w_c * scale_c >= 0) or the smallest one (< 0): each
+// thread keeps two numbers per point and evaluates C channels from them.  lane <-> point: every channel row is written
+// as 128 contiguous bytes per warp.
+__global__ void __launch_bounds__(256)
+edge_angle_max_kernel(const float* __restrict__ x, int64_t x_sb, int64_t x_sc, int64_t x_sn,
+                      const float* __restrict__ centroid, const int64_t* __restrict__ idx,
+                      const float* __restrict__ weight, const float* __restrict__ scale, const float* __restrict__ shift,
+                      float slope, int N, int k, int C, float* __restrict__ alpha_out, float* __restrict__ pooled) {
+    extern __shared__ __align__(16) float ea_sm[];
+    float* s_w = ea_sm;                      // [C][4]: w, scale, shift, pad
+    float* s_xyz = ea_sm + (size_t)C * 4;    // [N][3]
+    const int b = blockIdx.y, tid = threadIdx.x;
+    const float* xb = x + (int64_t)b * x_sb;
+    for (int e = tid; e < C; e += blockDim.x) {
+        s_w[e * 4] = weight[e]; s_w[e * 4 + 1] = scale[e]; s_w[e * 4 + 2] = shift[e]; s_w[e * 4 + 3] = 0.f;
+    }
+    for (int e = tid; e < 3 * N; e += blockDim.x) {
+        const int c = e / N, n = e - c * N;
+        s_xyz[3 * n + c] = xb[(int64_t)c * x_sc + (int64_t)n * x_sn];
+    }
+    __syncthreads();
+    const int n = blockIdx.x * blockDim.x + tid;
+    if (n >= N) return;
+    const float qx = s_xyz[3 * n], qy = s_xyz[3 * n + 1], qz = s_xyz[3 * n + 2];
+    // normalize(p2gc): three independent divisions by max(|v|, 1e-12), as F.normalize does
+    float gx = qx - centroid[3 * b], gy = qy - centroid[3 * b + 1], gz = qz - centroid[3 * b + 2];
+    {
+        const float gn = fmaxf(sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz))), 1e-12f);
+        gx = __fdiv_rn(gx, gn); gy = __fdiv_rn(gy, gn); gz = __fdiv_rn(gz, gn);
+    }
+    float amax = -INFINITY, amin = INFINITY;
+    const int64_t* ip = idx + ((int64_t)b * N + n) * k;
+    for (int kk = 0; kk < k; ++kk) {
+        int64_t j = ip[kk];
+        j = j < 0 ? 0 : (j >= N ? N - 1 : j);
+        float dx = s_xyz[3 * j] - qx, dy = s_xyz[3 * j + 1] - qy, dz = s_xyz[3 * j + 2] - qz;
+        const float dn = fmaxf(sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz))), 1e-12f);
+        dx = __fdiv_rn(dx, dn); dy = __fdiv_rn(dy, dn); dz = __fdiv_rn(dz, dn);
+        const float a = __fadd_rn(__fadd_rn(__fmul_rn(dx, gx), __fmul_rn(dy, gy)), __fmul_rn(dz, gz));
+        if (alpha_out != nullptr) alpha_out[((int64_t)b * N + n) * k + kk] = a;
+        amax = fmaxf(amax, a); amin = fminf(amin, a);
+    }
+    for (int c = 0; c < C; ++c) {
+        const float4 w = *reinterpret_cast<const float4*>(s_w + c * 4);
+        // the side that wins the max: the affine map has the sign of w * scale (LeakyReLU is increasing for slope >= 0)
+        const bool up = (w.x >= 0.f) == (w.y >= 0.f);
+        float v = fmaf(__fmul_rn(w.x, up ? amax : amin), w.y, w.z);
+        v = v >= 0.f ? v : __fmul_rn(v, slope);
+        pooled[((int64_t)b * C + c) * N + n] = v;
+    }
+}
+
 }  // namespace ogmm
 
 using namespace ogmm;
@@ -144,5 +207,30 @@ extern "C" __attribute__((visibility("default"))) int ogmm_edge_conv_max(
     else LAUNCH(32);
 #undef LAUNCH
     OGMM_LAUNCH_CHECK("edge_conv_max_kernel");
+    return OGMM_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int ogmm_edge_angle_max(
+    const float* x, int64_t x_sb, int64_t x_sc, int64_t x_sn, const float* centroid, const int64_t* idx, const float* weight,
+    const float* scale, const float* shift, float slope, int64_t B, int64_t N, int64_t k, int64_t C, float* alpha_out,
+    float* max_out, ogmm_stream_t stream) {
+    OGMM_REQUIRE(B >= 0 && N >= 1 && k >= 1 && C >= 1 && B < 65536 && N < (1ll << 24), OGMM_EINVAL,
+                 "ogmm_edge_angle_max: bad sizes B=%lld N=%lld k=%lld C=%lld", (long long)B, (long long)N, (long long)k, (long long)C);
+    OGMM_REQUIRE(slope >= 0.f, OGMM_EINVAL, "ogmm_edge_angle_max: negative LeakyReLU slope %g (the max shortcut needs a monotone activation)", (double)slope);
+    if (B == 0) return OGMM_OK;
+    OGMM_REQUIRE(x && centroid && idx && weight && scale && shift && max_out, OGMM_EINVAL, "ogmm_edge_angle_max: null pointer");
+    const size_t smem = sizeof(float) * ((size_t)C * 4 + (size_t)3 * N);
+    OGMM_REQUIRE(smem <= 200 * 1024, OGMM_EUNSUPPORTED, "ogmm_edge_angle_max: N=%lld, C=%lld need %zu B of shared memory", (long long)N,
+                 (long long)C, smem);
+    if (smem > 48 * 1024) {
+        int st = cuda_status(cudaFuncSetAttribute(edge_angle_max_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                             "cudaFuncSetAttribute(edge_angle_max_kernel)");
+        if (st != OGMM_OK) return st;
+    }
+    const int threads = 128;
+    dim3 grid((unsigned)((N + threads - 1) / threads), (unsigned)B);
+    edge_angle_max_kernel<<<grid, threads, smem, as_stream(stream)>>>(x, x_sb, x_sc, x_sn, centroid, idx, weight, scale, shift,
+                                                                      slope, (int)N, (int)k, (int)C, alpha_out, max_out);
+    OGMM_LAUNCH_CHECK("edge_angle_max_kernel");
     return OGMM_OK;
 }

@@ -131,6 +131,20 @@ def install(modules=None, model=None):
 
         cls.forward = forward
         done.append("models.dgcnn.DGCNN.forward")
+    # PositionEncoding.forward: the k = 5 angle feature (kNN graph + normalised offsets + conv_ang1 + max) in one kernel
+    # under the same conditions
+    at = sys.modules.get("models.attn")
+    if at is not None and (modules is None or "models.attn" in modules) and hasattr(at, "PositionEncoding"):
+        cls = at.PositionEncoding
+        orig_pe = _saved_methods.setdefault((cls, "forward"), cls.forward)
+
+        def pe_forward(self, points, k=5, _orig=orig_pe):
+            if self.training or _needs_grad((points,), {}) or (torch.is_grad_enabled() and any(p.requires_grad for p in self.conv_ang1.parameters())):
+                return _orig(self, points, k)
+            return _modules.position_encoding_forward(self, points, k)
+
+        cls.forward = pe_forward
+        done.append("models.attn.PositionEncoding.forward")
     if model is not None:
         for m in model.modules():
             for (mod_name, attr), orig in _saved.items():

@@ -16,7 +16,8 @@ from ._guard import forward_only
 from .se3 import compute_rigid_transformation
 from .utils import wkeans_plus
 
-__all__ = ["Clustering", "GMMSVD", "graph_features", "gmm_register", "deepgmr_em", "edge_conv1", "dgcnn_forward"]
+__all__ = ["Clustering", "GMMSVD", "graph_features", "gmm_register", "deepgmr_em", "edge_conv1", "dgcnn_forward",
+           "angle_conv1", "position_encoding_forward"]
 
 
 class Clustering(nn.Module):
@@ -122,3 +123,30 @@ def dgcnn_forward(self, x):
     x4 = x.max(dim=-1, keepdim=True)[0]
     x = torch.cat((x1, x2, x3, x4), dim=1)
     return F.relu(self.bn5(self.conv5(x))).view(batch_size, -1, num_points)
+
+
+@forward_only
+def angle_conv1(points, idx, conv, bn, slope=0.2, want_alpha=False):
+    """models/attn.py:65-73 in one launch, for inference: points (B,3,N), idx (B,N,k) (the k-NN graph of the points),
+    conv = Conv2d(1, C, 1, bias=False), bn = BatchNorm2d(C) in eval mode, LeakyReLU(slope)
+    -> (alpha (B,1,N,k) | None, max over k of leaky(bn(conv(alpha))) (B,C,N))."""
+    if bn.training:
+        raise RuntimeError("angle_conv1 folds BatchNorm's running statistics: the module must be in eval() mode")
+    scale, shift = _fold_bn(bn)
+    centroid = torch.mean(points, dim=-1)                                   # models/attn.py:65
+    alpha, pooled = ops.edge_angle_max(points, centroid, idx, conv.weight.reshape(-1), scale, shift, slope, want_alpha)
+    return (alpha.unsqueeze(1) if alpha is not None else None), pooled
+
+
+def position_encoding_forward(self, points, k=5):
+    """Drop-in body for ``PositionEncoding.forward`` (models/attn.py:58-77) in eval / no_grad mode: the distance branch is
+    the module's own PyTorch layers; the angle branch is the kNN graph (K1) and one fused kernel up to the max over k."""
+    centroid = torch.mean(points, dim=-1, keepdim=True)
+    g_dis = torch.square(points - centroid).sum(dim=1, keepdim=True)
+    dis_feature = self.conv_dis(g_dis)
+    pts = points.transpose(-1, -2)
+    idx = ops.knn_graph(pts, pts, k)[0]
+    act = self.conv_ang1[2]
+    _, pooled = angle_conv1(points, idx, self.conv_ang1[0], self.conv_ang1[1], slope=getattr(act, "negative_slope", 0.2))
+    ang_feature = self.conv_ang2(pooled)
+    return torch.cat([dis_feature, ang_feature], dim=1)

@@ -115,6 +115,30 @@ def edge_conv_max(x, idx, weight, scale, shift, want_act=True):
     return act, pooled
 
 
+def edge_angle_max(x, centroid, idx, weight, scale, shift, slope=0.2, want_alpha=False):
+    """x (B,3,N) view, centroid (B,3), idx (B,N,k) int64, weight / scale / shift (C) -> alpha (B,N,k) | None, pooled (B,C,N):
+    the angle feature of PositionEncoding (models/attn.py:65-73) through conv_ang1's 1x1 conv + BN + LeakyReLU + max."""
+    _need_cuda_f32("x", x); _need_cuda_f32("centroid", centroid)
+    _need_cuda_f32("weight", weight); _need_cuda_f32("scale", scale); _need_cuda_f32("shift", shift)
+    if idx.dtype != torch.int64 or not idx.is_cuda:
+        raise TypeError("edge_angle_max: idx must be a CUDA int64 tensor")
+    B, three, N = x.shape
+    k = idx.shape[-1]
+    C = weight.numel()
+    if three != 3 or tuple(idx.shape) != (B, N, k) or centroid.numel() != 3 * B or scale.numel() != C or shift.numel() != C:
+        raise ValueError("edge_angle_max: expected x (B,3,N), centroid (B,3), idx (B,N,k), weight / scale / shift (C)")
+    idx, centroid = idx.contiguous(), centroid.reshape(B, 3).contiguous()
+    weight, scale, shift = weight.reshape(C).contiguous(), scale.contiguous(), shift.contiguous()
+    alpha = torch.empty((B, N, k), dtype=torch.float32, device=x.device) if want_alpha else None
+    pooled = torch.empty((B, C, N), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        st = _lib.load().ogmm_edge_angle_max(x.data_ptr(), *x.stride(), centroid.data_ptr(), idx.data_ptr(), weight.data_ptr(),
+                                             scale.data_ptr(), shift.data_ptr(), float(slope), B, N, k, C, _ptr(alpha),
+                                             pooled.data_ptr(), _stream(x))
+    _lib.check(st, "ogmm_edge_angle_max")
+    return alpha, pooled
+
+
 def fps(xyz, npoint, start=None, want_points=False):
     """xyz (B,N,3) view -> ids (B,npoint) int64 [, points (B,npoint,3)].  start=None: is_center."""
     _need_cuda_f32("xyz", xyz)

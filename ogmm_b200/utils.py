@@ -177,24 +177,38 @@ def cos_similarity(x, y):
     return ops.cos_similarity(x, y)
 
 
-@forward_only
 def get_local_corrs(xyz, xyz_mu, feats):
-    """lib/utils.py:244-254.  Feature of the point nearest to each anchor: 1-NN through the kNN kernel."""
-    idx = ops.knn_graph(xyz_mu, xyz, 1)[0]                       # (B,S,1)
+    """lib/utils.py:244-254.  Feature of the point nearest to each anchor: 1-NN through the kNN kernel.
+
+    Autograd: the reference's graph -- the index comes from ``topk`` (no gradient), the features from ``torch.gather``,
+    so only ``feats`` receives a gradient (a scatter of the anchor gradients); the gather stays a torch op here too."""
+    with torch.no_grad():
+        idx = ops.knn_graph(xyz_mu.detach(), xyz.detach(), 1)[0]                       # (B,S,1)
     return torch.gather(feats, dim=1, index=idx.repeat(1, 1, feats.size(-1)))
 
 
-@forward_only
+get_local_corrs.ogmm_autograd_safe = True
+
+
 def get_anchor_corrs(xyz, feats, num_clusters, dst='eu', iters=10, is_fast=True):
-    """lib/utils.py:257-266, ``is_fast=True`` branch (the only one the model takes).  xyz (B,3,N), feats (B,D,N)."""
+    """lib/utils.py:257-266, ``is_fast=True`` branch (the only one the model takes).  xyz (B,3,N), feats (B,D,N).
+
+    Autograd as in the reference: FPS indices carry no gradient; the gathered features (and anchors, should ``xyz``
+    require grad) are index selections that torch differentiates."""
     if not is_fast:
         raise NotImplementedError("get_anchor_corrs(is_fast=False) has no live caller in the reference")
     xt, ft = xyz.transpose(-1, -2), feats.transpose(-1, -2)
     start = torch.randint(0, xt.shape[1], (xt.shape[0],), dtype=torch.long)
-    ids, xyz_mu = ops.fps(xt, num_clusters, start, want_points=True)
+    with torch.no_grad():
+        ids, xyz_mu = ops.fps(xt.detach(), num_clusters, start, want_points=True)
+    if _needs_grad(xt):
+        xyz_mu = index_points(xt, ids)
     feats_pos = index_points(ft, ids).transpose(-1, -2)
     feats_anchor = get_local_corrs(xt, xyz_mu, ft).transpose(-1, -2)
     return feats_anchor, feats_pos, xyz_mu.transpose(-1, -2)
+
+
+get_anchor_corrs.ogmm_autograd_safe = True
 
 
 def wkeans_plus(xyz, feats, o_scores, n_clusters, iters=10, tau=1.0):

@@ -93,7 +93,8 @@ def test_gmmreg_stage_outputs_inside_the_model(ref):
             seen.setdefault(name, []).append([o.detach().clone() for o in (out if isinstance(out, tuple) else (out,))])
         return hook
 
-    handles = [model.emd.register_forward_hook(grab("emd")), model.cluster.register_forward_hook(grab("cluster"))]
+    handles = [model.emd.register_forward_hook(grab("emd")), model.cluster.register_forward_hook(grab("cluster")),
+               model.pos.register_forward_hook(grab("pos"))]
     try:
         _run(model, src, tgt, 3)
         inst.install()
@@ -108,6 +109,10 @@ def test_gmmreg_stage_outputs_inside_the_model(ref):
     for a, b in zip(emd_ref, emd_new):
         e = float((a[0] - b[0]).abs().max() / a[0].abs().max())
         print(f"\n  DGCNN features (B,512,N): {e:.2e} relative")
+        assert e < 1e-4
+    for a, b in zip(seen["pos"][:2], seen["pos"][2:]):         # PositionEncoding: our kNN graph + fused angle feature
+        e = float((a[0] - b[0]).abs().max() / a[0].abs().max())
+        print(f"  PositionEncoding features (B,512,N): {e:.2e} relative")
         assert e < 1e-4
     for a, b in zip(seen["cluster"][:2], seen["cluster"][2:]):
         gam0, pi0, mu0, nf0 = a
@@ -195,7 +200,7 @@ def test_gmmreg_training_step_patched_equals_unpatched(ref):
             loss.backward()
         torch.cuda.synchronize()
         grads = {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
-        return rot, float(loss), grads
+        return rot, float(loss.detach()), grads
 
     rot0, loss0, g0 = step(7)
     _, loss0b, g0b = step(7)

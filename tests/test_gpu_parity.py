@@ -286,6 +286,44 @@ def test_edge_conv1_fused(og):
         modules.edge_conv1(x, idx, conv, bn)
 
 
+def test_angle_conv1_fused(og):
+    """N3, second half (models/attn.py:65-73): kNN offsets -> normalise -> cosine with the centred point -> conv_ang1
+    (Conv2d 1 -> C + BN eval + LeakyReLU 0.2) -> max over k in one kernel, against the same lines in PyTorch.  Weights
+    of both signs exercise the max / min shortcut."""
+    import torch.nn.functional as F
+    from ogmm_b200 import modules
+    g = torch.Generator().manual_seed(31)
+    for (b, n, k, c) in ((3, 1024, 5, 64), (2, 717, 5, 64), (2, 300, 9, 40), (1, 4096, 5, 64)):
+        x = cu(torch.rand(b, 3, n, generator=g) * 2 - 1)
+        x[0, :, 7] = x[0, :, 3]                                   # a duplicate point: a zero offset besides the self neighbour
+        conv = torch.nn.Conv2d(1, c, kernel_size=1, bias=False).cuda()
+        bn = torch.nn.BatchNorm2d(c).cuda()
+        with torch.no_grad():
+            conv.weight.copy_(cu(torch.randn(c, 1, 1, 1, generator=g)))
+            bn.running_mean.copy_(cu(torch.randn(c, generator=g) * 0.2))
+            bn.running_var.copy_(cu(torch.rand(c, generator=g) + 0.5))
+            bn.weight.copy_(cu(torch.randn(c, generator=g)))      # both signs
+            bn.bias.copy_(cu(torch.randn(c, generator=g) * 0.1))
+        bn.eval()
+        idx = og.knn(x.transpose(1, 2), x.transpose(1, 2), k)
+        with torch.no_grad(), torch.backends.cudnn.flags(enabled=False):
+            p2gc = x - torch.mean(x, dim=-1, keepdim=True)
+            p2lc = og.get_graph_feature(x, k, idx)[:, :3]
+            alpha_ref = torch.einsum('bdnk,bdn->bnk', F.normalize(p2lc, dim=1), F.normalize(p2gc, dim=1)).unsqueeze(1)
+            ref = F.leaky_relu(bn(conv(alpha_ref)), 0.2).max(dim=-1)[0]
+        alpha, pooled = modules.angle_conv1(x, idx, conv, bn, slope=0.2, want_alpha=True)
+        assert tuple(alpha.shape) == (b, 1, n, k) and tuple(pooled.shape) == (b, c, n)
+        e_a = float((alpha - alpha_ref).abs().max())
+        e_p = float((pooled - ref).abs().max() / ref.abs().max())
+        print(f"\n  angle_conv1 N={n} k={k} C={c}: alpha {e_a:.2e} abs (|alpha| <= 1), pooled {e_p:.2e} relative")
+        assert e_a < 1e-6 and e_p < 1e-5
+        # the shortcut is exact: pooling our own alpha through the same folded affine map gives the same bits
+        assert torch.equal(modules.angle_conv1(x, idx, conv, bn)[1], pooled)
+    bn.train()
+    with pytest.raises(RuntimeError, match="eval"):
+        modules.angle_conv1(x, idx, conv, bn)
+
+
 # ------------------------------------------------------------------------------------------ FPS
 def test_fps(og, orc, golden):
     g = golden("fps")
