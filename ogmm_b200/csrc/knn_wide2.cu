@@ -51,13 +51,6 @@ __device__ __forceinline__ void w2_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 // wait of the single-lane roles: back off between polls so the two spinning lanes leave the issue slots to the selectors
-// One staged pair: the value at shared-window address `addr`, its candidate index `idx_off` bytes further (explicit
-// st.shared so the hot loop carries a 32-bit address, not a generic pointer).
-__device__ __forceinline__ void w2_sts_pair(uint32_t addr, float v, int ix, uint32_t idx_off) {
-    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
-    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr + idx_off), "r"(ix) : "memory");
-}
-
 __device__ __forceinline__ void w2_wait_idle(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     while (true) {
@@ -256,7 +249,7 @@ knn_wide2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
 #pragma unroll
         for (int j = 0; j < K; ++j) best[j] = INFINITY;
         float bound = valid ? 3.0e38f : -INFINITY;      // collect bound: best[K-1] + 2E (finite so that padding +inf never passes)
-        int n_col = 0;
+        int n_st = 0, n_col = 0;
         const uint32_t tmem_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
         const int cols = BN / SEL, c_lo = half * cols;  // this thread's columns of every tile (a multiple of 32)
 
@@ -264,11 +257,7 @@ knn_wide2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
 #pragma unroll
         for (int j = 0; j < K; ++j) key[j] = kW2Empty;
         int overflow = 0;
-        // next free staging slot of this thread as a 32-bit shared-window address (index slot: + 4 * kW2Stage * kW2Sel bytes);
-        // the number staged is (sp - base) / (4 * kW2Sel): no counter and no 64-bit pointer arithmetic in the hot loop
-        const uint32_t sp_base = (uint32_t)__cvta_generic_to_shared(s_stage_v + st);
-        const uint32_t sp_trig = sp_base + 4u * kW2Trigger * kW2Sel;
-        uint32_t sp = sp_base;
+        float* sp = s_stage_v + st;                     // next free staging slot of this thread (index slot: + kW2Stage * kW2Sel)
         auto compact = [&]() {                          // keep the collected pairs at or below the current bound
             int w = 0;
             for (int e = 0; e < n_col; ++e) {
@@ -291,7 +280,6 @@ knn_wide2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             n_col = 0;
         };
         auto merge = [&]() {                            // warp-converged
-            const int n_st = (int)((sp - sp_base) / (4u * kW2Sel));
             // room for every staged pair first: compact against the current bound; a column that is still too full
             // (masses of near-ties) is emptied into the exact list, so nothing is ever dropped
             if (__any_sync(kFull, n_col + n_st > kW2Cap)) {
@@ -310,7 +298,8 @@ knn_wide2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 }
                 if (v <= bound) { s_col_v[n_col * kW2Sel + st] = v; s_col_i[n_col * kW2Sel + st] = ix; ++n_col; }
             }
-            sp = sp_base;
+            n_st = 0;
+            sp = s_stage_v + st;
             if (valid) bound = fminf(best[K - 1] + err2, 3.0e38f);
         };
 
@@ -338,11 +327,13 @@ knn_wide2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                     for (int u = 0; u < 8; ++u) {
                         const int i = 8 * g + u;
                         if (v[i] <= bound) {
-                            w2_sts_pair(sp, v[i], mb + i, 4u * kW2Stage * kW2Sel);
-                            sp += 4u * kW2Sel;
+                            sp[0] = v[i];
+                            reinterpret_cast<int*>(sp)[kW2Stage * kW2Sel] = mb + i;
+                            sp += kW2Sel;
+                            ++n_st;
                         }
                     }
-                    if (__any_sync(kFull, sp > sp_trig)) merge();
+                    if (__any_sync(kFull, n_st > kW2Trigger)) merge();
                 }
             }
         }
