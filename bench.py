@@ -585,13 +585,63 @@ def time_model_forward(dev, pairs=32, reps=3):
         t_new, out_new = best_of()
     finally:
         inst.uninstall()
+    train = time_model_train_step(dev, ref, refload, inst, synth)
     from tests_gpu_util import rot_err_deg
-    return {"pairs": pairs, "reference_ms": t_ref * 1e3, "patched_ms": t_new * 1e3, "reference_pairs_per_s": pairs / t_ref,
+    return {"train_step": train,
+            "pairs": pairs, "reference_ms": t_ref * 1e3, "patched_ms": t_new * 1e3, "reference_pairs_per_s": pairs / t_ref,
             "patched_pairs_per_s": pairs / t_new, "speedup": t_ref / t_new,
             "rot_deg_patched_vs_reference": float(rot_err_deg(out_new[0].cpu(), out_ref[0].cpu()).max()),
             "overlap_score_abs_diff": float((out_new[2] - out_ref[2]).abs().max()),
             "note": "whole model incl. the PyTorch DGCNN convolutions and transformer overlap detector that stay PyTorch in "
                     "both arms; random-init weights, eval(), no_grad, cuDNN disabled as in train.py:194-196, best of %d after 1 warm-up" % reps}
+
+
+def time_model_train_step(dev, ref, refload, inst, synth, pairs=8, reps=3):
+    """One training step of the unmodified GMMReg (train.py:53-75: forward in train() mode, registration + clustering +
+    overlap loss, backward), stock path vs after install() -- where the differentiable hot-path pieces (feature M-step,
+    soft-correspondence head, Procrustes / 3x3 SVD) run on the repo's forward and backward kernels."""
+    import torch
+    try:
+        torch.manual_seed(99)
+        model = ref["gmmreg"].GMMReg(512, 16, refload.model_config()).to(dev).train()
+        s, t, R_gt, t_gt = synth.modelnet_batch(100, pairs, 1024)
+        src, tgt = torch.from_numpy(s).to(dev), torch.from_numpy(t).to(dev)
+        rot_gt, trans_gt = torch.from_numpy(R_gt).to(dev).float(), torch.from_numpy(t_gt).to(dev).float().view(pairs, 3)
+        o_gt = (torch.rand(pairs, 2048, generator=torch.Generator().manual_seed(1)) > 0.4).float().to(dev)
+        loss_mod = ref["loss"]
+
+        def best_of():
+            best, gnorm, lossv = None, None, None
+            with torch.backends.cudnn.flags(enabled=False):
+                for i in range(reps + 1):
+                    model.zero_grad(set_to_none=True)
+                    torch.manual_seed(7)
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    rot, trans, src_o, tgt_o, clu = model(src, tgt)
+                    o_pred = torch.nan_to_num(torch.cat([src_o, tgt_o], dim=-1), nan=0.0).clip(min=0.0)
+                    loss = 10 * loss_mod.dcp_loss(rot, rot_gt, trans, trans_gt) + clu + loss_mod.get_weighted_bce_loss(o_pred, o_gt)
+                    loss.backward()
+                    torch.cuda.synchronize()
+                    dt = time.perf_counter() - t0
+                    if i > 0:
+                        best = dt if best is None else min(best, dt)
+                gnorm = float(sum(p.grad.double().pow(2).sum() for p in model.parameters() if p.grad is not None) ** 0.5)
+                lossv = float(loss.detach())
+            return best, gnorm, lossv
+
+        t_ref, g_ref, l_ref = best_of()
+        inst.install(model=model)
+        try:
+            t_new, g_new, l_new = best_of()
+        finally:
+            inst.uninstall()
+        return {"pairs": pairs, "reference_ms": t_ref * 1e3, "patched_ms": t_new * 1e3, "speedup": t_ref / t_new,
+                "loss_reference": l_ref, "loss_patched": l_new, "grad_norm_reference": g_ref, "grad_norm_patched": g_new,
+                "note": "forward (train mode) + loss + backward of the unmodified reference model, random-init weights, cuDNN "
+                        "disabled as in train.py:194-196, best of %d after 1 warm-up; no optimizer step" % reps}
+    except Exception as e:                                   # the forward figure must survive a failure here
+        return {"error": f"{type(e).__name__}: {e}"}
 
 
 # ----------------------------------------------------------------------------------------- our arm
