@@ -15,8 +15,8 @@
 // All CTAs therefore hold bit-identical totals (same values, same order), so the replicated per-column work (potential
 // update, centroid update, exit bookkeeping) needs no broadcast and every data-dependent branch is cluster-uniform.
 // The exchange buffer is double buffered by call parity: a CTA can run at most one all-reduce ahead of the slowest CTA,
-// so one cluster barrier per all-reduce is enough.  Cost per cloud: ~100 x (2 passes over 1024 x 64 entries per CTA,
-// MUFU bound: exp2 + sqrt per entry and pass) + ~270 cluster barriers of ~0.2 us.
+// so one cluster barrier per all-reduce is enough.  Cost per cloud: ~100 x (one sweep over 1024 x 64 entries per CTA,
+// MUFU bound: sqrt + exp2 per entry; the column sums reuse the row pass's exponentials) + ~270 cluster barriers of ~0.2 us.
 #include <cooperative_groups.h>
 
 #include "sinkhorn_impl.cuh"
@@ -43,9 +43,12 @@ struct DSmem {
     float* red;        // [32]
     float* misc;       // [16]
     unsigned long long* key;   // [32]
+    float4* cost;      // [kDCacheJ / 4][kDChunk] costs of the first kDCacheJ columns for this CTA's points (per outer iteration)
 };
-constexpr size_t kDSmemBytes = sizeof(float4) * kDMaxJ + sizeof(float) * (2 * kDMaxJ + 4 * (kDNT / 32) * kDMaxJ + 2 * kXW +
+constexpr int kDCacheJ = 40;                  // columns whose cost c_ij is cached in shared memory (160 KB at 1024 points; 54 KB are taken by the exchange buffers)
+constexpr size_t kDSmemSmall = sizeof(float4) * kDMaxJ + sizeof(float) * (2 * kDMaxJ + 4 * (kDNT / 32) * kDMaxJ + 2 * kXW +
                                                                            2 * kCS * kXW + 32 + 16) + sizeof(unsigned long long) * 32;
+constexpr size_t kDSmemBytes = ((kDSmemSmall + 15) & ~(size_t)15) + sizeof(float4) * (kDCacheJ / 4) * kDChunk;
 
 __device__ __forceinline__ DSmem carve_dsmem(unsigned char* raw) {
     DSmem s;
@@ -59,6 +62,7 @@ __device__ __forceinline__ DSmem carve_dsmem(unsigned char* raw) {
     s.red = s.slots + 2 * kCS * kXW;
     s.misc = s.red + 32;
     s.key = reinterpret_cast<unsigned long long*>(s.misc + 16);
+    s.cost = reinterpret_cast<float4*>(raw + ((kDSmemSmall + 15) & ~(size_t)15));
     return s;
 }
 
@@ -239,55 +243,88 @@ sinkhorn_cluster_dsmem_kernel(SinkhornParams P, int mode) {
         for (int p = 0; p < kDPPT; ++p) u[p] = 0.f;
         __syncthreads();
         for (int j = tid; j < kDMaxJ; j += kDNT) S.v[j] = 0.f;
+        // The centroids are fixed for the n_it iterations of this call: the cost of the first kDCacheJ columns is
+        // computed once and kept in shared memory as [column quad][point] float4 (consecutive lanes -> consecutive 16 B,
+        // conflict free; each thread reads back only what it wrote), the remaining columns are recomputed per iteration.
+#pragma unroll
+        for (int p = 0; p < kDPPT; ++p) {
+#pragma unroll
+            for (int q = 0; q < kDCacheJ / 4; ++q) {
+                if (4 * q < J) {
+                    float4 c4;
+                    c4.x = cost_at(p, 4 * q); c4.y = cost_at(p, 4 * q + 1); c4.z = cost_at(p, 4 * q + 2); c4.w = cost_at(p, 4 * q + 3);
+                    S.cost[(size_t)q * kDChunk + tid + p * kDNT] = c4;
+                }
+            }
+        }
         __syncthreads();
 
         for (int it = 0; it < n_it; ++it) {
-            // ---- row update: u_i += eps (log p_i - LSE_j K_ij), local to the point
+            // ---- row update u_i += eps (log p_i - LSE_j K_ij) and the column sums of the UPDATED kernel in ONE sweep per
+            // point.  With x_ij = (-c_ij + u_i + v_j) k2, m_i = max_j x_ij, e_ij = exp2(x_ij - m_i), s_i = sum_j e_ij the row
+            // update is u_i' = u_i + eps (log p_i - (m_i + log2 s_i) ln 2), and the column pass needs
+            //     exp2((-c_ij + u_i' + v_j) k2) = e_ij * exp2(m_i + (u_i' - u_i) k2)          (= e_ij p_i / s_i)
+            // i.e. the e_ij the row pass already holds times ONE more exp2 per point -- sqrt + exp2 once per entry and
+            // iteration instead of twice (the kernel is MUFU bound).  The 64 e_ij of the point stay in registers; the
+            // points of a thread are processed one after the other and their butterfly outputs add up.
             float du_abs = 0.f;
+            float tot4[kDMaxJ / kJC];
 #pragma unroll
+            for (int c = 0; c < kDMaxJ / kJC; ++c) tot4[c] = 0.f;
+#pragma unroll 1
             for (int p = 0; p < kDPPT; ++p) {
-                if (live[p]) {
-                    float m = -INFINITY, s = 0.f;
-                    for (int j0 = 0; j0 < J; j0 += kJC) {
-                        float x[kJC];
-                        float mc = -INFINITY;
+                float e[kDMaxJ];
+                const bool lv = p == 0 ? live[0] : live[1];
+                const float up = p == 0 ? u[0] : u[1], lp = p == 0 ? logp[0] : logp[1];
+                const float ax = p == 0 ? m2x[0] : m2x[1], ay = p == 0 ? m2y[0] : m2y[1], az = p == 0 ? m2z[0] : m2z[1];
+                const float an = p == 0 ? pn[0] : pn[1];
+                float un = up;
+                if (lv) {
+                    float m = -INFINITY;
 #pragma unroll
-                        for (int jj = 0; jj < kJC; ++jj) {
-                            const int j = j0 + jj;
-                            if (j < J) { x[jj] = __fadd_rn(__fadd_rn(-cost_at(p, j), u[p]), S.v[j]) * k2; mc = fmaxf(mc, x[jj]); }
-                            else x[jj] = -INFINITY;
-                        }
-                        const float mn = fmaxf(m, mc);
-                        float acc = 0.f;
+                    for (int q = 0; q < kDCacheJ / 4; ++q) {
+                        float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (4 * q < J) c4 = S.cost[(size_t)q * kDChunk + tid + p * kDNT];
+                        const float cq[4] = {c4.x, c4.y, c4.z, c4.w};
 #pragma unroll
-                        for (int jj = 0; jj < kJC; ++jj) acc += exp2f(x[jj] - mn);
-                        s = s * exp2f(m - mn) + acc;
-                        m = mn;
-                    }
-                    const float lse = (m + log2f(s)) * kLn2;
-                    const float un = __fadd_rn(__fmul_rn(P.eps, logp[p] - lse), u[p]);
-                    du_abs += fabsf(un - u[p]);
-                    u[p] = un;
-                }
-            }
-            // ---- column sums (no max shift needed after a row update), CTA partials -> cluster totals
-            for (int j0 = 0; j0 < J; j0 += kJC) {
-                float part[kJC];
-#pragma unroll
-                for (int jj = 0; jj < kJC; ++jj) part[jj] = 0.f;
-#pragma unroll
-                for (int p = 0; p < kDPPT; ++p) {
-                    if (live[p]) {
-#pragma unroll
-                        for (int jj = 0; jj < kJC; ++jj) {
-                            const int j = j0 + jj;
-                            if (j < J) part[jj] += exp2f(__fadd_rn(__fadd_rn(-cost_at(p, j), u[p]), S.v[j]) * k2);
+                        for (int t = 0; t < 4; ++t) {
+                            const int j = 4 * q + t;
+                            e[j] = -INFINITY;
+                            if (j < J) { e[j] = __fadd_rn(__fadd_rn(-cq[t], up), S.v[j]) * k2; m = fmaxf(m, e[j]); }
                         }
                     }
+#pragma unroll
+                    for (int j = kDCacheJ; j < kDMaxJ; ++j) {
+                        e[j] = -INFINITY;
+                        if (j < J) { e[j] = __fadd_rn(__fadd_rn(-node_cost(ax, ay, az, an, S.node[j], P.tau), up), S.v[j]) * k2; m = fmaxf(m, e[j]); }
+                    }
+                    float sum = 0.f;
+#pragma unroll
+                    for (int j = 0; j < kDMaxJ; ++j) { e[j] = exp2f(e[j] - m); sum += e[j]; }
+                    const float lse = (m + log2f(sum)) * kLn2;
+                    un = __fadd_rn(__fmul_rn(P.eps, lp - lse), up);
+                    du_abs += fabsf(un - up);
+                    const float w = exp2f(fmaf(un - up, k2, m));
+#pragma unroll
+                    for (int j = 0; j < kDMaxJ; ++j) e[j] *= w;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < kDMaxJ; ++j) e[j] = 0.f;
                 }
-                const float tot = butterfly16(part, lane);
-                if ((lane & 1) == 0) S.wtot[(size_t)warp * kDMaxJ + j0 + ((lane >> 1) & 15)] = tot;
+                if (p == 0) u[0] = un; else u[1] = un;
+#pragma unroll
+                for (int c = 0; c < kDMaxJ / kJC; ++c) {
+                    if (c * kJC < J) {                                    // cluster-uniform
+                        float part[kJC];
+#pragma unroll
+                        for (int jj = 0; jj < kJC; ++jj) part[jj] = e[c * kJC + jj];
+                        tot4[c] += butterfly16(part, lane);
+                    }
+                }
             }
+#pragma unroll
+            for (int c = 0; c < kDMaxJ / kJC; ++c)
+                if (c * kJC < J && (lane & 1) == 0) S.wtot[(size_t)warp * kDMaxJ + c * kJC + ((lane >> 1) & 15)] = tot4[c];
             du_abs = block_sum<kDNT>(du_abs, S.red);              // also orders the wtot writes before the fold
             fold_warps(S, 0, J, 0);
             if (tid == 0) S.loc[J] = du_abs;
