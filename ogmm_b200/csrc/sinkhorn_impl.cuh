@@ -189,7 +189,9 @@ fps_kernel(const float* __restrict__ xyz, int64_t sb, int64_t sn, int64_t sc, in
 
 // ---- cost ------------------------------------------------------------------------------------------------
 // c_ij = cdist(x_i, node_j).clip(0) / tau.  ATen _euclidean_dist: [-2x, |x|^2, 1] . [y, 1, |y|^2] in k order.
-__device__ __forceinline__ float node_cost(float m2x, float m2y, float m2z, float pn, const float4 c, float tau) {
+// cdist alone (tau == 1, how Clustering.forward calls wkeans_plus, models/gmmreg.py:28): callers that build a whole row
+// test tau once and pick this version, instead of one compare + select per entry.
+__device__ __forceinline__ float node_dist(float m2x, float m2y, float m2z, float pn, const float4 c) {
     float d2 = __fmul_rn(m2x, c.x);
     d2 = fmaf(m2y, c.y, d2);
     d2 = fmaf(m2z, c.z, d2);
@@ -197,6 +199,10 @@ __device__ __forceinline__ float node_cost(float m2x, float m2y, float m2z, floa
     d2 = __fadd_rn(d2, c.w);
     float d;
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(d) : "f"(fmaxf(d2, 0.f)));  // 1 ulp; clamp_min(0).sqrt()
+    return d;
+}
+__device__ __forceinline__ float node_cost(float m2x, float m2y, float m2z, float pn, const float4 c, float tau) {
+    const float d = node_dist(m2x, m2y, m2z, pn, c);
     return tau == 1.0f ? d : __fdiv_rn(d, tau);
 }
 
@@ -493,13 +499,22 @@ __device__ __forceinline__ void process_cloud(const SinkhornParams& P, const Sme
             // ---- scaled-domain iterations ------------------------------------------------------------------
             float wold[PPT];        // u_old - m_i, where u_i = m_i + eps log a_i
             reload_xyz();
+            const bool unit_tau = P.tau == 1.0f;                 // block-uniform: one branch per row instead of one select per entry
 #pragma unroll
             for (int p = 0; p < PPT; ++p) {
                 float mn = INFINITY;
+                if (unit_tau) {
 #pragma unroll
-                for (int j = 0; j < JF; ++j) {
-                    G[p][j] = j < J ? node_cost(m2x[p], m2y[p], m2z[p], pn[p], S.node[j], P.tau) : INFINITY;
-                    mn = fminf(mn, G[p][j]);
+                    for (int j = 0; j < JF; ++j) {
+                        G[p][j] = (kExactJ || j < J) ? node_dist(m2x[p], m2y[p], m2z[p], pn[p], S.node[j]) : INFINITY;
+                        mn = fminf(mn, G[p][j]);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < JF; ++j) {
+                        G[p][j] = (kExactJ || j < J) ? __fdiv_rn(node_dist(m2x[p], m2y[p], m2z[p], pn[p], S.node[j]), P.tau) : INFINITY;
+                        mn = fminf(mn, G[p][j]);
+                    }
                 }
 #pragma unroll
                 for (int j = 0; j < JF; ++j) G[p][j] = (tid + p * NT < N) ? fast_exp2((mn - G[p][j]) * k2) : 0.f;
