@@ -516,8 +516,11 @@ __device__ __forceinline__ void process_cloud(const SinkhornParams& P, const Sme
                         mn = fminf(mn, G[p][j]);
                     }
                 }
+                // a point past N gets -inf as its row minimum: every entry becomes exp2(-inf) = 0 without a select per entry
+                // (masked columns hold +inf and come out as 0 the same way)
+                const float mnx = (tid + p * NT < N) ? mn : -INFINITY;
 #pragma unroll
-                for (int j = 0; j < JF; ++j) G[p][j] = (tid + p * NT < N) ? fast_exp2((mn - G[p][j]) * k2) : 0.f;
+                for (int j = 0; j < JF; ++j) G[p][j] = fast_exp2((mnx - G[p][j]) * k2);
                 wold[p] = -mn;          // u_old = 0
                 a[p] = 0.f;
             }
