@@ -15,7 +15,7 @@
 // index -- the documented tie-break (torch.topk's own is unspecified).
 #include <stdlib.h>
 
-#include "common.cuh"
+#include "knn_common.cuh"
 
 namespace ogmm {
 
@@ -92,7 +92,10 @@ knn3_kernel(const float* __restrict__ src, int64_t s_sb, int64_t s_sn, int64_t s
             const float* __restrict__ dst, int64_t d_sb, int64_t d_sn, int64_t d_sc,
             int N, int M, int k, int normalize,
             int64_t* __restrict__ idx_out, float* __restrict__ dist_out, float* __restrict__ edge_out) {
-    __shared__ float4 s_cand[kCandTile];
+    // candidate tile as packed group records (knn_common.cuh: group_distances): 64 bytes per four candidates,
+    // (xA,xB,yA,yB) (zA,zB,wA,wB) (xC,xD,yC,yD) (zC,zD,wC,wD), coordinates pre-scaled by -2 -- two candidates per packed
+    // FP32x2 instruction, each half the same IEEE operation as the scalar form
+    __shared__ __align__(16) float s_rec[4 * kCandTile];
     __shared__ float s_stage_d[kStage * kKnnThreads];
     __shared__ int s_stage_i[kStage * kKnnThreads];
 
@@ -105,6 +108,9 @@ knn3_kernel(const float* __restrict__ src, int64_t s_sb, int64_t s_sn, int64_t s
     float qx = 0.f, qy = 0.f, qz = 0.f;
     if (valid) { qx = sb[(int64_t)q * s_sn]; qy = sb[(int64_t)q * s_sn + s_sc]; qz = sb[(int64_t)q * s_sn + 2 * s_sc]; }
     const float qs = normalize ? 2.0f : sq_norm3(qx, qy, qz);
+    QueryPack Q;
+    Q.x = pack2(qx, qx); Q.y = pack2(qy, qy); Q.z = pack2(qz, qz); Q.s = pack2(qs, qs);
+    const unsigned rec_base = (unsigned)__cvta_generic_to_shared(s_rec);
 
     TopK<K> top;
     top.init(s_stage_d, s_stage_i, kKnnThreads, tid, valid);
@@ -114,28 +120,31 @@ knn3_kernel(const float* __restrict__ src, int64_t s_sb, int64_t s_sn, int64_t s
         const int len4 = (len + 3) & ~3;
         __syncthreads();
         for (int m = tid; m < len4; m += kKnnThreads) {
-            float4 c = make_float4(0.f, 0.f, 0.f, INFINITY);
+            float x = 0.f, y = 0.f, z = 0.f, w = INFINITY;             // padding: distance +inf, never offered
             if (m < len) {
                 const float* p = db + (int64_t)(m0 + m) * d_sn;
-                const float x = p[0], y = p[d_sc], z = p[2 * d_sc];
-                c = make_float4(-2.f * x, -2.f * y, -2.f * z, normalize ? 0.f : sq_norm3(x, y, z));
+                const float cx = p[0], cy = p[d_sc], cz = p[2 * d_sc];
+                x = -2.f * cx; y = -2.f * cy; z = -2.f * cz; w = normalize ? 0.f : sq_norm3(cx, cy, cz);
             }
-            s_cand[m] = c;
+            float* r = s_rec + 16 * (m >> 2) + 8 * ((m & 3) >> 1) + (m & 1);
+            r[0] = x; r[2] = y; r[4] = z; r[6] = w;
         }
         __syncthreads();
         for (int m = 0; m < len4; m += 4) {
+            // (-2 s.d) accumulated like a K=3 GEMM, then + |s|^2, then + |d|^2 (lib/utils.py:28-32)
+            float v[4];
+            group_distances(rec_base + 16u * (unsigned)m, Q, v);
+            if (!normalize) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const float4 c = s_cand[m + u];
-                // (-2 s.d) accumulated like a K=3 GEMM, then + |s|^2, then + |d|^2 (lib/utils.py:28-32)
-                float v = __fmul_rn(qx, c.x);
-                v = fmaf(qy, c.y, v);
-                v = fmaf(qz, c.z, v);
-                v = __fadd_rn(__fadd_rn(v, qs), c.w);
-                if (!normalize) v = fmaxf(v, 1e-12f);
-                top.offer(v, m0 + m + u);
+                for (int u = 0; u < 4; ++u) v[u] = fmaxf(v[u], 1e-12f);
             }
-            top.maybe_merge();
+            // one test per group: after the first tiles a candidate beats the k-th best about once in a hundred
+            // (warp vote: the staged count only changes inside, so the merge test lives there too)
+            if (__any_sync(kFull, fminf(fminf(v[0], v[1]), fminf(v[2], v[3])) < top.thr)) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) top.offer(v[u], m0 + m + u);
+                top.maybe_merge();
+            }
         }
     }
     top.merge();

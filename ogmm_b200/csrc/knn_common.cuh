@@ -176,4 +176,43 @@ __device__ __forceinline__ float sqn3(float x, float y, float z) {
 
 __host__ __device__ inline int pow2_ge(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
+// ---- packed FP32x2 distances of a group of four candidates (shared by the selection and the exhaustive kernels) ----
+typedef unsigned long long u64t;
+
+__device__ __forceinline__ u64t pack2(float lo, float hi) {
+    return ((u64t)__float_as_uint(hi) << 32) | (u64t)__float_as_uint(lo);
+}
+__device__ __forceinline__ u64t mul2(u64t a, u64t b) { u64t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64t fma2(u64t a, u64t b, u64t c) { u64t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ u64t add2(u64t a, u64t b) { u64t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ float lo32(u64t v) { return __uint_as_float((unsigned)(v & 0xffffffffull)); }
+__device__ __forceinline__ float hi32(u64t v) { return __uint_as_float((unsigned)(v >> 32)); }
+
+struct QueryPack { u64t x, y, z, s; };     // (qx,qx), (qy,qy), (qz,qz), (|q|^2,|q|^2)
+
+// Distances of the four candidates of one group, unclamped, in the reference's operation order (two candidates per
+// packed instruction; each half is an independent IEEE fp32 operation, so the values equal the scalar kernels' bit for
+// bit).  Record layout per group (64 bytes): (xA,xB,yA,yB) (zA,zB,wA,wB) (xC,xD,yC,yD) (zC,zD,wC,wD), coordinates
+// pre-scaled by -2.  `rec_addr` is the SHARED-window byte address of the group's record (explicit ld.shared: the
+// generic-pointer form re-derives the window base with S2R + LEA at every use).
+__device__ __forceinline__ void lds_pair(unsigned addr, u64t& a, u64t& b) {
+    asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr));
+}
+__device__ __forceinline__ void group_distances(unsigned rec_addr, const QueryPack& q, float (&v)[4]) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        u64t xx, yy, zz, ww;
+        lds_pair(rec_addr + 32 * h, xx, yy);
+        lds_pair(rec_addr + 32 * h + 16, zz, ww);
+        u64t d = mul2(q.x, xx);
+        d = fma2(q.y, yy, d);
+        d = fma2(q.z, zz, d);
+        d = add2(d, q.s);
+        d = add2(d, ww);
+        v[2 * h] = lo32(d);
+        v[2 * h + 1] = hi32(d);
+    }
+}
+
+
 }  // namespace ogmm
