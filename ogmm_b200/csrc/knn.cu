@@ -117,9 +117,9 @@ knn3_kernel(const float* __restrict__ src, int64_t s_sb, int64_t s_sn, int64_t s
 
     for (int m0 = 0; m0 < M; m0 += kCandTile) {
         const int len = min(kCandTile, M - m0);
-        const int len4 = (len + 3) & ~3;
+        const int len8 = (len + 7) & ~7;
         __syncthreads();
-        for (int m = tid; m < len4; m += kKnnThreads) {
+        for (int m = tid; m < len8; m += kKnnThreads) {
             float x = 0.f, y = 0.f, z = 0.f, w = INFINITY;             // padding: distance +inf, never offered
             if (m < len) {
                 const float* p = db + (int64_t)(m0 + m) * d_sn;
@@ -130,19 +130,25 @@ knn3_kernel(const float* __restrict__ src, int64_t s_sb, int64_t s_sn, int64_t s
             r[0] = x; r[2] = y; r[4] = z; r[6] = w;
         }
         __syncthreads();
-        for (int m = 0; m < len4; m += 4) {
-            // (-2 s.d) accumulated like a K=3 GEMM, then + |s|^2, then + |d|^2 (lib/utils.py:28-32)
-            float v[4];
+        // eight candidates (two group records) per step; (-2 s.d) accumulated like a K=3 GEMM, then + |s|^2, then + |d|^2
+        // (lib/utils.py:28-32).  Tiles are padded to a multiple of eight with +inf records.
+        for (int m = 0; m < len8; m += 8) {
+            float v[4], w[4];
             group_distances(rec_base + 16u * (unsigned)m, Q, v);
+            group_distances(rec_base + 16u * (unsigned)m + 64u, Q, w);
             if (!normalize) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u) v[u] = fmaxf(v[u], 1e-12f);
+                for (int u = 0; u < 4; ++u) { v[u] = fmaxf(v[u], 1e-12f); w[u] = fmaxf(w[u], 1e-12f); }
             }
-            // one test per group: after the first tiles a candidate beats the k-th best about once in a hundred
-            // (warp vote: the staged count only changes inside, so the merge test lives there too)
-            if (__any_sync(kFull, fminf(fminf(v[0], v[1]), fminf(v[2], v[3])) < top.thr)) {
+            // one test per step: after the first tiles a candidate beats the k-th best about once in a hundred
+            // (warp vote: the staged count only changes inside, so the merge tests live there too)
+            const float mn = fminf(fminf(fminf(v[0], v[1]), fminf(v[2], v[3])), fminf(fminf(w[0], w[1]), fminf(w[2], w[3])));
+            if (__any_sync(kFull, mn < top.thr)) {
 #pragma unroll
                 for (int u = 0; u < 4; ++u) top.offer(v[u], m0 + m + u);
+                top.maybe_merge();
+#pragma unroll
+                for (int u = 0; u < 4; ++u) top.offer(w[u], m0 + m + 4 + u);
                 top.maybe_merge();
             }
         }
