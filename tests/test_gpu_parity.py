@@ -918,6 +918,21 @@ def test_largest_supported_sizes(og, orc):
     assert relerr(pi, rpi) < 1e-4 and float((mu.cpu() - rmu).abs().max()) < 1e-4
 
 
+def test_fps_above_8192_points(og, orc):
+    """FPS for clouds the register kernel cannot hold (shared-memory kernel, N <= 16384): the anchors of
+    get_anchor_corrs (km_clusters = 128, random start) and the is_center start at cfg 4's cloud size, ragged N too."""
+    g = torch.Generator().manual_seed(12)
+    for n, npoint in ((16384, 128), (9001, 64), (12345, 16)):
+        x = torch.rand(2, n, 3, generator=g) * torch.tensor([1.0, 0.6, 0.3])
+        assert torch.equal(og.farthest_point_sample(cu(x), npoint, True).cpu(), orc.fps_indices(x, npoint, True))
+        start = torch.randint(0, n, (2,), generator=g)
+        ids, pts = og.ops.fps(cu(x), npoint, start, want_points=True)
+        assert torch.equal(ids.cpu(), orc.fps_indices(x, npoint, False, start))
+        assert torch.equal(pts.cpu(), torch.gather(x, 1, ids.cpu()[:, :, None].expand(-1, -1, 3)))
+    with pytest.raises(RuntimeError, match="ogmm_fps"):
+        og.ops.fps(cu(torch.rand(1, 16385, 3)), 4)
+
+
 def test_two_devices_from_two_threads_like_dataparallel(og):
     """nn.DataParallel (train.py:191) runs the forward from one Python thread per device in ONE process: the library must
     launch on the caller's current device and keep no per-process kernel configuration.  Needs two GPUs."""
