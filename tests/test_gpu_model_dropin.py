@@ -220,3 +220,26 @@ def test_gmmreg_training_step_patched_equals_unpatched(ref):
           f"{len(g0)} parameter tensors")
     assert abs(loss1 - loss0) <= 1e-3 * max(abs(loss0), 1e-6)
     assert num / den < 2e-2 and worst[0] < 5e-2
+
+
+def test_gmmreg_forward_large_cloud(ref):
+    """The same drop-in check on one pair of 9000-point clouds: above 8192 points the patched forward runs the
+    shared-memory FPS kernel, the exhaustive 3-D kNN and the 16-CTA-cluster Sinkhorn k-means (cfg 4's code paths)."""
+    from oracle import refload
+    import ogmm_b200.install as inst
+    torch.manual_seed(2024)
+    model = ref["gmmreg"].GMMReg(512, 16, refload.model_config()).cuda().eval()
+    src, tgt = _pairs(1, 9000, seed=5)
+    rot0, t0, so0, to0, _ = _run(model, src, tgt, 11)
+    inst.install(model=model)
+    try:
+        rot1, t1, so1, to1, _ = _run(model, src, tgt, 11)
+    finally:
+        inst.uninstall()
+    e_rot = float(rot_err_deg(rot1.cpu(), rot0.cpu()).max())
+    scale = float(torch.maximum(src.abs().max(), tgt.abs().max()))
+    e_t = float((t1 - t0).abs().max()) / scale
+    e_o = float(torch.maximum((so1 - so0).abs().max(), (to1 - to0).abs().max()))
+    print(f"\n  GMMReg.forward patched vs unpatched (B=1, N=9000, J=16): rot {e_rot:.2e} deg, trans {e_t:.2e} of scale, "
+          f"overlap scores {e_o:.2e} abs")
+    assert tuple(so1.shape) == (1, 9000) and e_o < 1e-3 and e_rot < 0.1 and e_t < 1e-3
