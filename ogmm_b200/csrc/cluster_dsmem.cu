@@ -112,6 +112,7 @@ sinkhorn_cluster_dsmem_kernel(SinkhornParams P, int mode) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int N = P.N, J = P.J, iters = P.iters, max_iter = P.max_iter;
     const float k2 = (1.0f / P.eps) * kLog2e;
+    const bool unit_tau = P.tau == 1.0f;
     const bool first = mode == 0;
     int resume = 0;
     if (!first) {
@@ -293,10 +294,18 @@ sinkhorn_cluster_dsmem_kernel(SinkhornParams P, int mode) {
                             if (j < J) { e[j] = __fadd_rn(__fadd_rn(-cq[t], up), S.v[j]) * k2; m = fmaxf(m, e[j]); }
                         }
                     }
+                    if (unit_tau) {                                     // cluster-uniform: tau tested once, not per entry
 #pragma unroll
-                    for (int j = kDCacheJ; j < kDMaxJ; ++j) {
-                        e[j] = -INFINITY;
-                        if (j < J) { e[j] = __fadd_rn(__fadd_rn(-node_cost(ax, ay, az, an, S.node[j], P.tau), up), S.v[j]) * k2; m = fmaxf(m, e[j]); }
+                        for (int j = kDCacheJ; j < kDMaxJ; ++j) {
+                            e[j] = -INFINITY;
+                            if (j < J) { e[j] = __fadd_rn(__fadd_rn(-node_dist(ax, ay, az, an, S.node[j]), up), S.v[j]) * k2; m = fmaxf(m, e[j]); }
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = kDCacheJ; j < kDMaxJ; ++j) {
+                            e[j] = -INFINITY;
+                            if (j < J) { e[j] = __fadd_rn(__fadd_rn(-__fdiv_rn(node_dist(ax, ay, az, an, S.node[j]), P.tau), up), S.v[j]) * k2; m = fmaxf(m, e[j]); }
+                        }
                     }
                     float sum = 0.f;
 #pragma unroll
