@@ -19,7 +19,6 @@ from __future__ import annotations
 
 import os
 import sys
-import types
 
 import numpy as np
 import torch
