@@ -171,3 +171,34 @@ def test_rigid_transform_backward_reflection_branch(dev):
     ((R * gR).sum() + (t * gt).sum()).backward()
     for x, a in zip(xs, xs64):
         assert _rel(x.grad, a.grad) < 2e-4
+
+
+def test_backward_edge_shapes(dev):
+    """Odd and degenerate shapes: descriptor length not a multiple of 4, a single component (the covariance is just the
+    1e-5 I regulariser: equal singular values), an empty batch, and a descriptor row of zeros (F.normalize's clamp)."""
+    from oracle import ogmm_oracle as orc
+    from ogmm_b200 import ops
+    g = torch.Generator().manual_seed(77)
+    for (B, Js, Jt, D) in ((2, 7, 9, 3), (3, 1, 1, 8), (2, 1, 5, 6)):
+        ms, mt = torch.randn(B, Js, 3, generator=g).to(dev), torch.randn(B, Jt, 3, generator=g).to(dev)
+        fs, ft = torch.randn(B, Js, D, generator=g).to(dev), torch.randn(B, Jt, D, generator=g).to(dev)
+        gR, gt, gc = (torch.randn(s, generator=g).to(dev) for s in ((B, 3, 3), (B, 3), (B, 3, Js)))
+        ours = ops.soft_procrustes_backward(ms, mt, fs, ft, gR, gt, gc)
+        assert all(bool(torch.isfinite(o).all()) for o in ours)
+        if Js > 1:                                   # with one component R is the SVD of 1e-5 I: any gauge, gradients ill-defined
+            arb = _ref_head_grads(orc, ms, mt, fs, ft, gR, gt, gc, torch.float64)
+            r32 = _ref_head_grads(orc, ms, mt, fs, ft, gR, gt, gc, torch.float32)
+            for name, o, a, r in zip(("src_mu", "tgt_mu", "src_desc", "tgt_desc"), ours, arb, r32):
+                within_bar(_rel(o, a), 1e-4, _rel(r, a), f"d/d{name} (B={B}, Js={Js}, Jt={Jt}, D={D})")
+    # empty batch
+    e = ops.soft_procrustes_backward(torch.zeros(0, 4, 3, device=dev), torch.zeros(0, 4, 3, device=dev), torch.zeros(0, 4, 8, device=dev),
+                                     torch.zeros(0, 4, 8, device=dev), None, None, None)
+    assert tuple(e[2].shape) == (0, 4, 8)
+    es = ops.rigid_transform_backward(torch.zeros(0, 3, 5, device=dev), torch.zeros(0, 3, 5, device=dev), torch.zeros(0, 1, 5, device=dev), None, None)
+    assert tuple(es[0].shape) == (0, 3, 5)
+    # a zero descriptor row: x / max(|x|, 1e-12) is linear there; gradients stay finite
+    ms, mt = torch.randn(1, 4, 3, generator=g).to(dev), torch.randn(1, 4, 3, generator=g).to(dev)
+    fs, ft = torch.randn(1, 4, 8, generator=g).to(dev), torch.randn(1, 4, 8, generator=g).to(dev)
+    fs[0, 2] = 0.0
+    out = ops.soft_procrustes_backward(ms, mt, fs, ft, torch.randn(1, 3, 3, generator=g).to(dev), torch.randn(1, 3, generator=g).to(dev), None)
+    assert all(bool(torch.isfinite(o).all()) for o in out)
