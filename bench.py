@@ -867,7 +867,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(wl.config(B), launch=("cuda_graph_replay (one two-stream step per graph)" if graphed is not None
+            "config": dict(wl.config(B), launch=("cuda_graph_replay (one multi-stream step per graph: src / tgt chains on two streams, the kNN graphs on two more when a clustering launch cannot fill the GPU)" if graphed is not None
                                                  else (graph_note or "eager, two streams") if not args.no_overlap
                                                  else "eager, one stream")),
             "roofline": roofline, "roofline_hbm": roofline_hbm, "em_step": em, "kernels": kernels,
