@@ -220,7 +220,32 @@ def deepgmr_hot_path(src, tgt, src_logits, tgt_logits, k=20, timers=None, overla
         return edge, pi, mu, sigma
 
     cur = torch.cuda.current_stream(src.device)
-    if overlap:
+    if overlap and _split_schedule(src):
+        # small batches / large clouds: the E+M kernels and the kNN graphs are independent, four streams (see register_hot_path)
+        def em_chain(x, logits):
+            with _Stage(timers, "softmax_em"):
+                return ops.softmax_moments(logits, x, want_gamma=False)[1:]
+
+        def graph_chain(x):
+            pts = x.transpose(-1, -2)
+            with _Stage(timers, "knn_edge"):
+                return ops.knn_graph(pts, pts, k, want_edge=True)[2].permute(0, 3, 1, 2)
+
+        s_t, g_s, g_t = (_side_stream(src.device, i) for i in range(3))
+        for st in (s_t, g_s, g_t):
+            st.wait_stream(cur)
+        pi_s, mu_s, sg_s = em_chain(src, src_logits)
+        with torch.cuda.stream(s_t):
+            pi_t, mu_t, sg_t = em_chain(tgt, tgt_logits)
+        with torch.cuda.stream(g_s):
+            edge_s = graph_chain(src)
+        with torch.cuda.stream(g_t):
+            edge_t = graph_chain(tgt)
+        for st in (s_t, g_s, g_t):
+            cur.wait_stream(st)
+        for t in (edge_s, edge_t, pi_t, mu_t, sg_t):
+            t.record_stream(cur)
+    elif overlap:
         side = _side_stream(src.device)
         side.wait_stream(cur)
         with torch.cuda.stream(side):

@@ -811,6 +811,31 @@ def test_register_from_host_matches_device_path(og):
     assert h2d == sum(v.numel() * 4 for v in pinned.values()) and d2h == 24 * 12 * 4
 
 
+def test_step_schedules_agree(og, monkeypatch):
+    """The three ways a step is spread over streams -- one stream, the two-stream chain per cloud, the four-stream
+    schedule with the kNN graphs next to the clustering chains -- return the same bits, eagerly and from a CUDA graph,
+    for the OGMM path and the DeepGMR path (small batch: the automatic choice is the four-stream schedule)."""
+    from ogmm_b200 import pipeline, synth
+    h = synth.hot_path_inputs(3, 6, 1024, 128)
+    keys = ("src", "tgt", "src_feats", "tgt_feats", "src_o", "tgt_o")
+    d = {k: torch.from_numpy(np.ascontiguousarray(h[k])).float().cuda() for k in keys}
+    logits = [cu(torch.randn(6, 16, 1024, generator=torch.Generator().manual_seed(s))) for s in (1, 2)]
+    serial = pipeline.register_hot_path(*(d[k] for k in keys), 16, 20, overlap=False)
+    serial_d = pipeline.deepgmr_hot_path(d["src"], d["tgt"], logits[0], logits[1], 20, overlap=False)
+    torch.cuda.synchronize()
+    for mode in ("pair", "split", "auto"):
+        monkeypatch.setenv("OGMM_SCHEDULE", mode)
+        out = pipeline.register_hot_path(*(d[k] for k in keys), 16, 20)
+        out_d = pipeline.deepgmr_hot_path(d["src"], d["tgt"], logits[0], logits[1], 20)
+        g = pipeline.GraphedHotPath(*(d[k] for k in keys), 16, 20)
+        rep = g.replay()
+        torch.cuda.synchronize()
+        for name in ("rot", "trans", "edge_src", "edge_tgt", "src_gamma", "tgt_mu", "tgt_node_feats"):
+            assert torch.equal(out[name], serial[name]) and torch.equal(rep[name], serial[name]), (mode, name)
+        for name in ("transform", "edge_tgt", "src_sigma", "tgt_mu"):
+            assert torch.equal(out_d[name], serial_d[name]), (mode, name)
+
+
 def test_host_boundary_matches_register_from_host(og):
     """pipeline.HostBoundary (xyz + overlap scores from pinned host memory, features resident, one graph launch per step)
     returns exactly what the eager host-buffer entry point returns, also for new inputs written into the same buffers."""
