@@ -262,6 +262,21 @@ int ogmm_cos_similarity(const float* x, const float* y, int64_t B, int64_t N, in
 int ogmm_gmm_register(const float* pi_s, const float* mu_s, const float* mu_t, const float* sigma_t,
                       int64_t B, int64_t J, float* transform_out, ogmm_stream_t stream);
 
+/* Backward of the DeepGMR path (baseline/deepgmr.py:64-79 under training): the transform's gradient flows through
+ * gmm_register into (pi, mu, sigma) and through the xyz moments into gamma = softmax(logits).
+ *   ogmm_gmm_register_backward: inputs as ogmm_gmm_register; grad_transform (B,4,4) (the bottom row is ignored);
+ *   outputs grad_pi_s (B,J), grad_mu_s, grad_mu_t (B,J,3), grad_sigma_t (B,J,3,3), contiguous.
+ *   ogmm_gmm_moments_backward: dL/dgamma of lib/utils.py:130-149 on 3-D points.  pts (B,N,3) strided (b,n,c); pi (B,J),
+ *   mu (B,J,3), sigma (B,J,3,3) or NULL as the forward returned them; grad_pi / grad_mu / grad_sigma upstream (each may be
+ *   NULL); grad_gamma (B,N,J) written with the given element strides (b,n,j).  J <= 1024. */
+int ogmm_gmm_register_backward(const float* pi_s, const float* mu_s, const float* mu_t, const float* sigma_t,
+                               int64_t B, int64_t J, const float* grad_transform, float* grad_pi_s, float* grad_mu_s,
+                               float* grad_mu_t, float* grad_sigma_t, ogmm_stream_t stream);
+int ogmm_gmm_moments_backward(const float* pts, int64_t p_sb, int64_t p_sn, int64_t p_sc, const float* pi,
+                              const float* mu, const float* sigma, const float* grad_pi, const float* grad_mu,
+                              const float* grad_sigma, int64_t B, int64_t N, int64_t J, float* grad_gamma,
+                              int64_t o_sb, int64_t o_sn, int64_t o_sj, ogmm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

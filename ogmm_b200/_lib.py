@@ -49,6 +49,8 @@ SIGNATURES = {
     "ogmm_gmm_moments_feat_ws": (i32, [c_f, i64, i64, i64, c_f, i64, i64, i64, i64, i64, i64, i64, c_f, c_f, vp, i64, vp]),
     "ogmm_gmm_moments_feat_backward": (i32, [c_f, i64, i64, i64, c_f, c_f, i64, i64, i64, i64, c_f, i64, i64, i64, vp]),
     "ogmm_softmax_moments": (i32, [c_f, c_f, i64, i64, i64, i64, i64, i64, c_f, c_f, c_f, c_f, vp]),
+    "ogmm_gmm_moments_backward": (i32, [c_f, i64, i64, i64, c_f, c_f, c_f, c_f, c_f, c_f, i64, i64, i64, c_f, i64, i64, i64, vp]),
+    "ogmm_gmm_register_backward": (i32, [c_f, c_f, c_f, c_f, i64, i64, c_f, c_f, c_f, c_f, c_f, vp]),
     "ogmm_rigid_transform": (i32, [c_f, i64, i64, i64, c_f, i64, i64, i64, c_f, i64, i64, i64, i64, c_f, c_f, vp]),
     "ogmm_soft_procrustes": (i32, [c_f, c_f, c_f, c_f, i64, i64, i64, i64, f32, c_f, c_f, c_f, c_f, vp]),
     "ogmm_rigid_transform_backward": (i32, [c_f, i64, i64, i64, c_f, i64, i64, i64, c_f, i64, i64, i64, i64, c_f, c_f,

@@ -1,6 +1,7 @@
 """Backward support for the differentiable pieces of the path the reference trains through (SURVEY.md section 8(f)
 N4): the feature M-step ``node_feats = gmm_params(gamma, feats)[1]`` (lib/utils.py:289), the soft-correspondence head
-``GMMSVD(is_sk=False)`` (models/dgcnn.py:96-115) and ``compute_rigid_transformation`` (lib/se3.py:256-289).
+``GMMSVD(is_sk=False)`` (models/dgcnn.py:96-115) and ``compute_rigid_transformation`` (lib/se3.py:256-289); and the
+DeepGMR path: the xyz moments with sigma as a function of gamma and ``gmm_register`` (baseline/deepgmr.py:17-38, :71-75).
 
 In the reference's training step (train.py:57-75) the Sinkhorn loop runs under ``no_grad`` and ``gamma`` is detached
 (lib/utils.py:275-286), so autograd enters the clustering only through ``feats``:
@@ -79,6 +80,45 @@ class RigidTransform(torch.autograd.Function):
         src, corr, weight = ctx.saved_tensors
         g = ops.rigid_transform_backward(src, corr, weight, _f32(grad_rot), _f32(grad_t))
         return tuple(gi if need else None for gi, need in zip(g, ctx.needs_input_grad))
+
+
+class NarrowMoments(torch.autograd.Function):
+    """gmm_params(gamma, pts[, return_sigma]) on 3-D points, differentiable with respect to gamma (how DeepGMR trains:
+    gamma = softmax(logits), baseline/deepgmr.py:71-74).  Backward = ``ogmm_gmm_moments_backward``."""
+
+    @staticmethod
+    def forward(ctx, gamma, pts, return_sigma):
+        out = ops.gmm_moments(gamma, pts, return_sigma)
+        ctx.save_for_backward(pts, *out)
+        ctx.like = gamma
+        return out
+
+    @staticmethod
+    def backward(ctx, *grads):
+        pts, pi, mu, *rest = ctx.saved_tensors
+        sigma = rest[0] if rest else None
+        g_pi, g_mu = grads[0], grads[1]
+        g_sigma = grads[2] if len(grads) > 2 else None
+        return ops.gmm_moments_backward(pts, pi, mu, sigma, _f32(g_pi), _f32(g_mu), _f32(g_sigma), ctx.like), None, None
+
+
+class GmmRegister(torch.autograd.Function):
+    """baseline/deepgmr.py:17-38 -> T (B,4,4).  Backward = ``ogmm_gmm_register_backward``."""
+
+    @staticmethod
+    def forward(ctx, pi_s, mu_s, mu_t, sigma_t):
+        ctx.save_for_backward(pi_s, mu_s, mu_t, sigma_t)
+        return ops.gmm_register(pi_s, mu_s, mu_t, sigma_t)
+
+    @staticmethod
+    def backward(ctx, grad_tf):
+        g = ops.gmm_register_backward(*ctx.saved_tensors, grad_tf.float())
+        return tuple(gi if need else None for gi, need in zip(g, ctx.needs_input_grad))
+
+
+def can_differentiate_narrow(gamma, pts, return_sigma=False):
+    """True for the xyz-moments call DeepGMR differentiates: 3-D points without grad, gamma with grad."""
+    return pts.dim() == 3 and pts.shape[-1] == 3 and not pts.requires_grad
 
 
 def _f32(g):

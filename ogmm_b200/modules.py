@@ -77,10 +77,16 @@ def graph_features(x, k=20):
     return ops.knn_graph(pts, pts, k, want_edge=True)[2].permute(0, 3, 1, 2)
 
 
-@forward_only
 def gmm_register(pi_s, mu_s, mu_t, sigma_t):
-    """baseline/deepgmr.py:17-38 -> (B,4,4); no host SVD and no hard-coded ``.cuda()``."""
-    return ops.gmm_register(pi_s, mu_s, mu_t, sigma_t)
+    """baseline/deepgmr.py:17-38 -> (B,4,4); no host SVD and no hard-coded ``.cuda()``.  Differentiable (backward kernel
+    ``ogmm_gmm_register_backward``) when autograd records the call."""
+    if autograd.records(pi_s, mu_s, mu_t, sigma_t):
+        return autograd.GmmRegister.apply(pi_s, mu_s, mu_t, sigma_t)
+    with torch.no_grad():
+        return ops.gmm_register(pi_s, mu_s, mu_t, sigma_t)
+
+
+gmm_register.ogmm_autograd_safe = True
 
 
 @forward_only

@@ -252,6 +252,51 @@ def gmm_moments_feat_backward(gamma, grad_mu, pi, like):
     return out
 
 
+def gmm_moments_backward(pts, pi, mu, sigma, grad_pi, grad_mu, grad_sigma, like):
+    """dL/dgamma of the xyz moments ``gmm_moments(gamma, pts, return_sigma)`` (D = 3): pts (B,N,3) view, pi (B,J), mu (B,J,3),
+    sigma (B,J,3,3) | None, upstream gradients (each may be None) -> grad_gamma with the shape AND strides of ``like``
+    (B,N,J) (DeepGMR holds gamma as the transposed view of a (B,J,N) tensor)."""
+    _need_cuda_f32("pts", pts); _need_cuda_f32("pi", pi); _need_cuda_f32("mu", mu)
+    B, N, three = pts.shape
+    J = pi.shape[1]
+    if three != 3 or tuple(mu.shape) != (B, J, 3) or tuple(like.shape) != (B, N, J):
+        raise ValueError("gmm_moments_backward: expected pts (B,N,3), pi (B,J), mu (B,J,3), gamma-like (B,N,J)")
+    pi, mu = pi.contiguous(), mu.contiguous()
+    sigma = sigma.contiguous() if sigma is not None else None
+    gs = []
+    for n_, g, shape in (("grad_pi", grad_pi, (B, J)), ("grad_mu", grad_mu, (B, J, 3)), ("grad_sigma", grad_sigma, (B, J, 3, 3))):
+        if g is not None:
+            _need_cuda_f32(n_, g)
+            g = g.reshape(shape).contiguous()
+        gs.append(g)
+    transposed = like.stride(1) == 1 and like.stride(2) >= N               # a transposed view of (B,J,N)
+    out = torch.empty((B, J, N), dtype=torch.float32, device=pts.device).transpose(1, 2) if transposed else \
+        torch.empty((B, N, J), dtype=torch.float32, device=pts.device)
+    with torch.cuda.device(pts.device):
+        st = _lib.load().ogmm_gmm_moments_backward(pts.data_ptr(), *pts.stride(), pi.data_ptr(), mu.data_ptr(), _ptr(sigma),
+                                                   _ptr(gs[0]), _ptr(gs[1]), _ptr(gs[2]), B, N, J, out.data_ptr(),
+                                                   *out.stride(), _stream(pts))
+    _lib.check(st, "ogmm_gmm_moments_backward")
+    return out
+
+
+def gmm_register_backward(pi_s, mu_s, mu_t, sigma_t, grad_transform):
+    """Gradients of ``gmm_register``: grad_transform (B,4,4) -> grad_pi_s (B,J), grad_mu_s, grad_mu_t (B,J,3),
+    grad_sigma_t (B,J,3,3)."""
+    for n_, t_ in (("pi_s", pi_s), ("mu_s", mu_s), ("mu_t", mu_t), ("sigma_t", sigma_t), ("grad_transform", grad_transform)):
+        _need_cuda_f32(n_, t_)
+    B, J = pi_s.shape
+    pi_s, mu_s, mu_t, sigma_t = (t_.contiguous() for t_ in (pi_s, mu_s, mu_t, sigma_t))
+    grad_transform = grad_transform.reshape(B, 4, 4).contiguous()
+    g_pi, g_ms, g_mt, g_sg = (torch.empty_like(t_) for t_ in (pi_s, mu_s, mu_t, sigma_t))
+    with torch.cuda.device(pi_s.device):
+        st = _lib.load().ogmm_gmm_register_backward(pi_s.data_ptr(), mu_s.data_ptr(), mu_t.data_ptr(), sigma_t.data_ptr(), B, J,
+                                                    grad_transform.data_ptr(), g_pi.data_ptr(), g_ms.data_ptr(),
+                                                    g_mt.data_ptr(), g_sg.data_ptr(), _stream(pi_s))
+    _lib.check(st, "ogmm_gmm_register_backward")
+    return g_pi, g_ms, g_mt, g_sg
+
+
 def softmax_moments(logits, pts, want_gamma=True):
     """logits (B,J,N), pts (B,3,N) view -> gamma (B,J,N) | None, pi (B,J), mu (B,J,3), sigma (B,J,3,3)."""
     _need_cuda_f32("logits", logits); _need_cuda_f32("pts", pts)

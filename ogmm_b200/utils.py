@@ -129,11 +129,14 @@ def gmm_params(gamma, pts, return_sigma=False):
 
     Wide features (D > 4, no sigma) go through ``shared_moments``: the call ``CluLoss`` makes right after
     ``wkeans_plus`` on the same tensors returns the result already computed (the returned tensors are shared: treat
-    them as read-only, as both reference callers do).  The same wide call is differentiable with respect to ``pts``
-    (``ogmm_b200/autograd.py``); any other call that autograd would have to record is refused."""
+    them as read-only, as both reference callers do).  The same wide call is differentiable with respect to ``pts``, and
+    the xyz call (3-D points, with or without sigma) with respect to ``gamma`` (``ogmm_b200/autograd.py``); any other call
+    that autograd would have to record is refused."""
     if _needs_grad(gamma, pts):
         if autograd.can_differentiate(gamma, pts, return_sigma):
             return autograd.feature_moments(gamma, pts)
+        if autograd.can_differentiate_narrow(gamma, pts, return_sigma):          # DeepGMR: moments of xyz as a function of gamma
+            return autograd.NarrowMoments.apply(gamma, pts, bool(return_sigma))
         raise RuntimeError("ogmm_b200.gmm_params is forward-only for this call (sigma, narrow points or a gamma that requires "
                            "grad): its kernels have no backward.  Call it under torch.no_grad() or keep the reference function.")
     with torch.no_grad():
@@ -142,7 +145,8 @@ def gmm_params(gamma, pts, return_sigma=False):
         return ops.gmm_moments(gamma, pts, return_sigma)
 
 
-gmm_params.ogmm_can_differentiate = lambda gamma, pts, return_sigma=False: autograd.can_differentiate(gamma, pts, return_sigma)
+gmm_params.ogmm_can_differentiate = lambda gamma, pts, return_sigma=False: (
+    autograd.can_differentiate(gamma, pts, return_sigma) or autograd.can_differentiate_narrow(gamma, pts, return_sigma))
 
 
 @forward_only

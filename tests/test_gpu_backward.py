@@ -202,3 +202,58 @@ def test_backward_edge_shapes(dev):
     fs[0, 2] = 0.0
     out = ops.soft_procrustes_backward(ms, mt, fs, ft, torch.randn(1, 3, 3, generator=g).to(dev), torch.randn(1, 3, generator=g).to(dev), None)
     assert all(bool(torch.isfinite(o).all()) for o in out)
+
+
+@pytest.mark.parametrize("B,N,J,with_sigma", [(3, 1024, 16, True), (2, 717, 5, True), (2, 300, 16, False), (1, 4096, 40, True)])
+def test_narrow_moments_backward_vs_reference_autograd(dev, B, N, J, with_sigma):
+    """gmm_params(gamma, xyz, return_sigma) differentiated with respect to gamma = softmax(logits), as DeepGMR trains it
+    (baseline/deepgmr.py:71-74): through the public function, gamma held as the transposed view of a (B,J,N) tensor."""
+    from oracle import ogmm_oracle as orc
+    import ogmm_b200 as og
+    g = torch.Generator().manual_seed(N + J)
+    logits = torch.randn(B, J, N, generator=g).to(dev)
+    pts = (torch.randn(B, 3, N, generator=g) * torch.tensor([1.0, 0.5, 0.25])[None, :, None]).to(dev)
+    ups = [torch.randn(s, generator=g).to(dev) for s in ((B, J), (B, J, 3), (B, J, 3, 3))]
+
+    def run(fn, dtype):
+        lg = logits.detach().to(dtype).requires_grad_(True)
+        gam = torch.softmax(lg, dim=1).transpose(-1, -2)                     # (B,N,J) view of (B,J,N)
+        out = fn(gam, pts.to(dtype).transpose(-1, -2), with_sigma)
+        loss = sum((o * u.to(dtype)).sum() for o, u in zip(out, ups))
+        loss.backward()
+        return lg.grad, out
+
+    ours, out = run(og.gmm_params, torch.float32)
+    assert out[1].grad_fn is not None and "NarrowMoments" in type(out[1].grad_fn).__name__
+    arb, _ = run(orc.gmm_moments, torch.float64)
+    r32, _ = run(orc.gmm_moments, torch.float32)
+    print()
+    within_bar(_rel(ours, arb), 1e-4, _rel(r32, arb), f"d/dlogits through the xyz moments (B={B}, N={N}, J={J}, sigma={with_sigma})")
+
+
+def test_gmm_register_backward_vs_reference_autograd(dev):
+    from oracle import ogmm_oracle as orc
+    import ogmm_b200 as og
+    g = torch.Generator().manual_seed(8)
+    for (B, J) in ((5, 16), (3, 7), (2, 40)):
+        pi = torch.softmax(torch.randn(B, J, generator=g), -1).to(dev)
+        ms = torch.randn(B, J, 3, generator=g).to(dev)
+        Rgt = torch.linalg.qr(torch.randn(B, 3, 3, generator=g))[0].to(dev)
+        mt = ms @ Rgt.transpose(1, 2) + 0.1 * torch.randn(B, J, 3, generator=g).to(dev) + torch.randn(B, 1, 3, generator=g).to(dev)
+        a = torch.randn(B, J, 3, 3, generator=g) * 0.2
+        sg = (a @ a.transpose(-1, -2) + 0.3 * torch.eye(3)).to(dev)
+        gT = torch.randn(B, 4, 4, generator=g).to(dev)
+
+        def run(fn, dtype):
+            xs = [x.detach().to(dtype).requires_grad_(True) for x in (pi, ms, mt, sg)]
+            T = fn(*xs)
+            (T * gT.to(dtype)).sum().backward()
+            return [x.grad for x in xs], T
+
+        ours, T = run(og.gmm_register, torch.float32)
+        assert "GmmRegister" in type(T.grad_fn).__name__
+        arb, _ = run(orc.deepgmr_register, torch.float64)
+        r32, _ = run(orc.deepgmr_register, torch.float32)
+        print()
+        for name, o, a_, r in zip(("pi_s", "mu_s", "mu_t", "sigma_t"), ours, arb, r32):
+            within_bar(_rel(o, a_), 1e-4, _rel(r, a_), f"gmm_register d/d{name} (B={B}, J={J}) vs fp64 autograd")
