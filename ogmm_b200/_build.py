@@ -17,7 +17,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libogmm_b200.so")
-SOURCES = ["capi.cu", "knn.cu", "knn_sweep.cu", "knn_select.cu", "knn_wide.cu", "knn_wide2.cu", "edge_conv.cu", "cluster.cu", "cluster_dsmem.cu", "sinkhorn.cu", "moments.cu", "moments_tc.cu", "moments_tma.cu", "moments_bwd.cu", "procrustes.cu", "procrustes_bwd.cu", "deepgmr_bwd.cu"]
+SOURCES = ["capi.cu", "knn.cu", "knn_sweep.cu", "knn_select.cu", "knn_tiles.cu", "knn_wide.cu", "knn_wide2.cu", "edge_conv.cu", "cluster.cu", "cluster_dsmem.cu", "sinkhorn.cu", "moments.cu", "moments_tc.cu", "moments_tma.cu", "moments_bwd.cu", "procrustes.cu", "procrustes_bwd.cu", "deepgmr_bwd.cu"]
 # translation units whose kernels launch a follow-up grid from the device (CUDA dynamic parallelism): relocatable
 # device code + the device runtime at link time
 RDC_SOURCES = {"cluster.cu", "cluster_dsmem.cu", "sinkhorn.cu"}

@@ -454,6 +454,9 @@ int ogmm_launch_knn_wide(const float* src, int64_t s_sb, int64_t s_sn, int64_t s
                          int64_t B, int64_t N, int64_t M, int64_t C, int64_t k, int normalize,
                          int64_t* idx_out, float* dist_out, int32_t* stats, cudaStream_t s);
 
+int ogmm_launch_knn3_tiles(const float* src, int64_t s_sb, int64_t s_sn, int64_t s_sc, int64_t B, int64_t M, int64_t k,
+                           int64_t* idx_out, float* dist_out, float* edge_out, cudaStream_t s);
+
 extern "C" __attribute__((visibility("default"))) int ogmm_knn_graph(const float* src, int64_t s_sb, int64_t s_sn, int64_t s_sc,
                               const float* dst, int64_t d_sb, int64_t d_sn, int64_t d_sc,
                               int64_t B, int64_t N, int64_t M, int64_t C, int64_t k, int normalize,
@@ -482,6 +485,15 @@ extern "C" __attribute__((visibility("default"))) int ogmm_knn_graph(const float
         if (!(force && force[0] == '1'))
             return ogmm_launch_knn3_sweep(src, s_sb, s_sn, s_sc, dst, d_sb, d_sn, d_sc, B, N, M, k, idx_out, dist_out,
                                           edge_out, s);
+    }
+    // large 3-D self graphs (4096 < N <= 16384): pre-sort + tiled sorted sweep (knn_tiles.cu); the exhaustive kernel below
+    // for two-cloud calls, the cosine form and larger clouds (and with OGMM_KNN_EXHAUSTIVE=1, same results)
+    if (C == 3 && !normalize && N == M && src == dst && s_sb == d_sb && s_sn == d_sn && s_sc == d_sc && M > 4096) {
+        const char* force = getenv("OGMM_KNN_EXHAUSTIVE");
+        if (!(force && force[0] == '1')) {
+            const int st = ogmm_launch_knn3_tiles(src, s_sb, s_sn, s_sc, B, M, k, idx_out, dist_out, edge_out, s);
+            if (st != OGMM_EUNSUPPORTED) return st;
+        }
     }
     // feature-space graphs (32 <= C <= 256, k <= 32): Gram tiles on the tensor cores (knn_wide.cu), exact FP32 re-rank;
     // OGMM_KNN_NO_TENSOR=1 forces the FP32 FMA kernel (bit-identical results; for A/B checks)

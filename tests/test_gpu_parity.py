@@ -220,6 +220,39 @@ def test_knn_cfg4_size(og):
     print(f"\n  N=16384: decidable rows xyz {f:.3f}, C=64 {fw:.3f}")
 
 
+def test_knn_tiled_sweep_equals_exhaustive(og, monkeypatch):
+    """Large 3-D self graphs (4096 < N <= 16384) go through the pre-sort + tiled sorted sweep (knn_tiles.cu); the
+    exhaustive kernel (OGMM_KNN_EXHAUSTIVE=1) is the bit-for-bit yardstick: indices, distances and edge features, on
+    uniform, surface-like, planar, clustered and duplicated clouds, ragged sizes, several k."""
+    from ogmm_b200 import synth
+    g = torch.Generator().manual_seed(2026)
+    clouds = []
+    src, _, _, _ = synth.modelnet_batch(7, 2, 16384)
+    clouds.append(("surface 16384", torch.from_numpy(src).transpose(1, 2).contiguous(), 20))
+    clouds.append(("uniform 9001", torch.rand(2, 9001, 3, generator=g), 20))
+    clouds.append(("uniform 4097", torch.rand(1, 4097, 3, generator=g), 24))
+    plane = torch.rand(1, 8192, 3, generator=g); plane[:, :, 2] = 0.25
+    clouds.append(("plane 8192", plane, 5))
+    centres = torch.rand(1, 12, 3, generator=g)
+    clus = centres[:, torch.randint(0, 12, (12000,), generator=g)] + 0.01 * torch.randn(1, 12000, 3, generator=g)
+    clouds.append(("clustered 12000", clus, 16))
+    dup = torch.rand(1, 6000, 3, generator=g); dup[:, 3000:] = dup[:, :3000]         # every point twice: ties by index
+    clouds.append(("duplicates 6000", dup, 8))
+    line = torch.zeros(1, 5000, 3); line[:, :, 1] = torch.rand(1, 5000, generator=g)  # widest axis = y, x = z = 0
+    clouds.append(("line 5000", line, 20))
+    for name, x, k in clouds:
+        xc = cu(x)
+        monkeypatch.delenv("OGMM_KNN_EXHAUSTIVE", raising=False)
+        idx, dist, edge = og.ops.knn_graph(xc, xc, k, want_dist=True, want_edge=True)
+        monkeypatch.setenv("OGMM_KNN_EXHAUSTIVE", "1")
+        ref = og.ops.knn_graph(xc, xc, k, want_dist=True, want_edge=True)
+        assert torch.equal(idx, ref[0]), name
+        assert torch.equal(dist, ref[1]), name
+        assert torch.equal(edge, ref[2]), name
+        assert int(idx.min()) >= 0 and int(idx.max()) < x.shape[1]
+    monkeypatch.delenv("OGMM_KNN_EXHAUSTIVE", raising=False)
+
+
 def test_cluster_cfg4_size(og, orc):
     """BASELINE.json configs[3] at its own size: wkeans_plus on 16384 points with J = 64, iteration trace included."""
     from ogmm_b200 import synth
