@@ -28,13 +28,34 @@ constexpr float kTsBig = 1.0e38f;              // |c|^2 of padding positions: fi
 // workspace per cloud (floats): rec [Mp * 4] | key [Mp] | ord [Mp] (int) | meta [4]
 __host__ __device__ inline size_t tile_ws_floats(int Mp) { return (size_t)Mp * 6 + 4; }
 
-__global__ void __launch_bounds__(kSwThreads)
+constexpr int kPsThreads = 1024;                // the pre-sort is one CTA per cloud: as many threads as a CTA can have
+
+// (key, index) bitonic sort in shared memory, ascending, lexicographic; n a power of two (knn_common.cuh's version is
+// written for the 256-thread kernels).
+__device__ __forceinline__ void presort_pairs(float* key, int* val, int n) {
+    for (int k = 2; k <= n; k <<= 1) {
+        for (int j = k >> 1, lj = 31 - __clz(k >> 1); j > 0; j >>= 1, --lj) {
+            for (int t = threadIdx.x; t < (n >> 1); t += kPsThreads) {
+                const int i = ((t >> lj) << (lj + 1)) + (t & (j - 1));
+                const int l = i + j;
+                const bool up = ((i & k) == 0);
+                const float a = key[i], b = key[l];
+                const int ai = val[i], bi = val[l];
+                const bool a_gt_b = (a > b) || (a == b && ai > bi);
+                if (a_gt_b == up) { key[i] = b; key[l] = a; val[i] = bi; val[l] = ai; }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kPsThreads)
 knn3_presort_kernel(const float* __restrict__ dst, int64_t d_sb, int64_t d_sn, int64_t d_sc, int M, int Mp,
                     float* __restrict__ ws) {
     extern __shared__ __align__(16) unsigned char ps_raw[];
     float* s_key = reinterpret_cast<float*>(ps_raw);               // [Mp]
     int* s_ord = reinterpret_cast<int*>(s_key + Mp);               // [Mp]
-    __shared__ float s_red[kSwThreads / 32 * 8];
+    __shared__ float s_red[kPsThreads / 32 * 8];
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float* db = dst + (int64_t)b * d_sb;
     float* w = ws + (size_t)b * tile_ws_floats(Mp);
@@ -44,7 +65,7 @@ knn3_presort_kernel(const float* __restrict__ dst, int64_t d_sb, int64_t d_sn, i
     float* w_meta = reinterpret_cast<float*>(w_ord + Mp);
 
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY}, nmax = 0.f;
-    for (int m = tid; m < M; m += kSwThreads) {
+    for (int m = tid; m < M; m += kPsThreads) {
         const float* p = db + (int64_t)m * d_sn;
         const float x = p[0], y = p[d_sc], z = p[2 * d_sc];
         lo[0] = fminf(lo[0], x); hi[0] = fmaxf(hi[0], x);
@@ -65,18 +86,18 @@ knn3_presort_kernel(const float* __restrict__ dst, int64_t d_sb, int64_t d_sn, i
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
         float l = INFINITY, h = -INFINITY;
-        for (int ww = 0; ww < kSwThreads / 32; ++ww) { l = fminf(l, s_red[ww * 8 + a]); h = fmaxf(h, s_red[ww * 8 + 3 + a]); }
+        for (int ww = 0; ww < kPsThreads / 32; ++ww) { l = fminf(l, s_red[ww * 8 + a]); h = fmaxf(h, s_red[ww * 8 + 3 + a]); }
         ext[a] = h - l;
     }
-    for (int ww = 0; ww < kSwThreads / 32; ++ww) cn_max = fmaxf(cn_max, s_red[ww * 8 + 6]);
+    for (int ww = 0; ww < kPsThreads / 32; ++ww) cn_max = fmaxf(cn_max, s_red[ww * 8 + 6]);
     const int axis = (ext[0] >= ext[1] && ext[0] >= ext[2]) ? 0 : (ext[1] >= ext[2] ? 1 : 2);
-    for (int m = tid; m < Mp; m += kSwThreads) {
+    for (int m = tid; m < Mp; m += kPsThreads) {
         s_key[m] = m < M ? sort_key(db[(int64_t)m * d_sn + (int64_t)axis * d_sc]) : INFINITY;
         s_ord[m] = m < M ? m : 0x7fffffff;
     }
     __syncthreads();
-    bitonic_sort_pairs(s_key, s_ord, Mp);
-    for (int p = tid; p < Mp; p += kSwThreads) {
+    presort_pairs(s_key, s_ord, Mp);
+    for (int p = tid; p < Mp; p += kPsThreads) {
         float x = 0.f, y = 0.f, z = 0.f, wv = kTsBig;
         if (p < M) {
             const float* c = db + (int64_t)s_ord[p] * d_sn;
@@ -208,7 +229,7 @@ int ogmm_launch_knn3_tiles(const float* src, int64_t s_sb, int64_t s_sn, int64_t
     st = cuda_status(cudaFuncSetAttribute(knn3_presort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem),
                      "cudaFuncSetAttribute(knn3_presort_kernel)");
     if (st == OGMM_OK) {
-        knn3_presort_kernel<<<(unsigned)B, kSwThreads, sort_smem, s>>>(src, s_sb, s_sn, s_sc, (int)M, Mp, ws);
+        knn3_presort_kernel<<<(unsigned)B, kPsThreads, sort_smem, s>>>(src, s_sb, s_sn, s_sc, (int)M, Mp, ws);
         st = cuda_status(cudaGetLastError(), "knn3_presort_kernel");
     }
     if (st == OGMM_OK) {
