@@ -149,13 +149,15 @@ knn3_tile_sweep_kernel(const float* __restrict__ src, int64_t s_sb, int64_t s_sn
     TopK64<K> top;
     top.init(s_stage_d, s_stage_i, tid, valid);
 
-    auto process = [&](int t) {                             // all threads; tile t of the sorted cloud
+    auto process = [&](int t, bool mine) {                  // all threads; tile t of the sorted cloud; `mine`: this lane needs it
         __syncthreads();                                    // previous tile fully consumed
         const float4* g_rec = reinterpret_cast<const float4*>(w_rec + (size_t)t * kTsTile * 4);
         float4* s4 = reinterpret_cast<float4*>(s_rec);
         for (int e = tid; e < kTsTile; e += kSwThreads) s4[e] = __ldg(g_rec + e);
         for (int e = tid; e < kTsTile; e += kSwThreads) s_ord[e] = (unsigned short)w_ord[(size_t)t * kTsTile + e];
         __syncthreads();
+        // a warp whose 32 queries (neighbours along the axis) are all out of reach of this tile sits it out
+        if (!__any_sync(kFull, mine)) return;
         for (int m = 0; m < kTsTile; m += 8) {
             float v[4], u[4];
             group_distances(rec_base + 16u * (unsigned)m, Q, v);
@@ -177,7 +179,7 @@ knn3_tile_sweep_kernel(const float* __restrict__ src, int64_t s_sb, int64_t s_sn
 
     const int n_tiles = Mp / kTsTile;
     const int c = p0 / kTsTile;
-    process(c);
+    process(c, true);
     int l = c - 1, r = c + 1;
     while (true) {
         const float tl = top.thr * (1.0f + 1e-6f) + margin;
@@ -187,8 +189,11 @@ knn3_tile_sweep_kernel(const float* __restrict__ src, int64_t s_sb, int64_t s_sn
         const bool go_l = __syncthreads_or(need_l ? 1 : 0) != 0;      // (the builtin returns "any", not the OR of the values)
         const bool go_r = __syncthreads_or(need_r ? 1 : 0) != 0;
         if (!go_l && !go_r) break;
-        if (go_l) { process(l); --l; } else l = -1;         // a side nobody needs any more stays closed (thr only shrinks)
-        if (go_r) { process(r); ++r; } else r = n_tiles;
+        if (go_l) { process(l, need_l); --l; } else l = -1; // a side nobody needs any more stays closed (thr only shrinks)
+        if (go_r) {                                         // (the left tile may have tightened thr: test again, cheaply)
+            if (go_l && need_r) { const float g = w_key[(size_t)r * kTsTile] - qk; const float t2 = top.thr * (1.0f + 1e-6f) + margin; need_r = !(g > 0.f && g * g > t2); }
+            process(r, need_r); ++r;
+        } else r = n_tiles;
     }
 
     if (!valid) return;
