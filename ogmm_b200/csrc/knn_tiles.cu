@@ -22,7 +22,7 @@
 
 namespace ogmm {
 
-constexpr int kTsTile = 1024;                  // candidates per tile (256 group records, 16 KB)
+constexpr int kTsTile = 512;                   // candidates per tile (128 group records, 8 KB)
 constexpr float kTsBig = 1.0e38f;              // |c|^2 of padding positions: finite, above any real distance
 
 // workspace per cloud (floats): rec [Mp * 4] | key [Mp] | ord [Mp] (int) | meta [4]
