@@ -8,7 +8,7 @@
 //                            cloud is written to the workspace IN SORTED ORDER as packed group records (knn_common.cuh),
 //                            with the sorted axis keys and the sorted-position -> original-index map.
 //   knn3_tile_sweep_kernel   one CTA per 256 consecutive sorted queries (neighbours in space along the axis).  The CTA
-//                            walks the sorted cloud in tiles of 1024 candidates outwards from its own tile, left and
+//                            walks the sorted cloud in tiles of 256 candidates outwards from its own tile, left and
 //                            right alternately, each tile staged in shared memory and consumed like the exhaustive
 //                            kernel's (packed FP32x2 distances, eight candidates per warp vote, sorted 64-bit
 //                            (distance, index) lists).  A side is abandoned as soon as NO query of the CTA can still be
@@ -22,7 +22,7 @@
 
 namespace ogmm {
 
-constexpr int kTsTile = 512;                   // candidates per tile (128 group records, 8 KB)
+constexpr int kTsTile = 256;                   // candidates per tile (64 group records, 4 KB)
 constexpr float kTsBig = 1.0e38f;              // |c|^2 of padding positions: finite, above any real distance
 
 // workspace per cloud (floats): rec [Mp * 4] | key [Mp] | ord [Mp] (int) | meta [4]
