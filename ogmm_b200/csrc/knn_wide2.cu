@@ -57,7 +57,7 @@ __device__ __forceinline__ void w2_wait_idle(uint64_t* bar, uint32_t parity) {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
         if (ok) break;
-        __nanosleep(64);
+        __nanosleep(512);
     }
 }
 __device__ __forceinline__ void w2_arrive(uint64_t* bar) {
