@@ -309,7 +309,7 @@ sinkhorn_cluster_dsmem_kernel(SinkhornParams P, int mode) {
                     }
                     float sum = 0.f;
 #pragma unroll
-                    for (int j = 0; j < kDMaxJ; ++j) { e[j] = exp2f(e[j] - m); sum += e[j]; }
+                    for (int j = 0; j < kDMaxJ; ++j) { e[j] = fast_exp2(e[j] - m); sum += e[j]; }      // MUFU.EX2, ftz: no range fix-up code per entry
                     const float lse = (m + log2f(sum)) * kLn2;
                     un = __fadd_rn(__fmul_rn(P.eps, lp - lse), up);
                     du_abs += fabsf(un - up);
