@@ -193,9 +193,12 @@ class Flagship:
                          "ModelNet40-shape partial-overlap pairs, 1024 pts (BASELINE.json configs[1])")
         self.input_names = ("src", "tgt", "src_feats", "tgt_feats", "src_o", "tgt_o") + (("src_wide", "tgt_wide") if self.C else ())
         self.hbm_stage, self.hbm_kernel = "feat_moments", "gmm_moments_feat_tma_kernel" if cfg == 2 else "gmm_moments_feat kernels"
-        self.stage_kernels = {"knn_edge": "knn3 kernel (distance + top-k + edge write)", "knn_wide": "knn_wide_kernel (tcgen05)",
-                              "cluster": "sinkhorn_kernel (FPS + Sinkhorn k-means)", "feat_moments": self.hbm_kernel,
-                              "procrustes": "soft_procrustes kernel"}
+        self.stage_kernels = {"knn_edge": ("knn3_select_kernel<20> (distance + top-k + edge write)" if cfg == 2 else
+                                           "knn3_presort_kernel + knn3_tile_sweep_kernel<20> (distance + top-k + edge write)"),
+                              "knn_wide": "knn_wide2_kernel<20,2> (TMA + tcgen05)",
+                              "cluster": ("sinkhorn_kernel<256,4,...> (FPS + Sinkhorn k-means, one CTA per cloud)" if cfg == 2 else
+                                          "sinkhorn_cluster_dsmem_kernel (FPS + Sinkhorn k-means, one 16-CTA cluster per cloud)"),
+                              "feat_moments": self.hbm_kernel, "procrustes": "soft_procrustes_full_kernel"}
 
     def host_inputs(self, first, pairs, distinct):
         import numpy as np
@@ -367,7 +370,7 @@ class DeepGMRPath:
                      "(J=16), gmm_register; ICL-NUIM-shape pairs with density variation, 1024 pts (BASELINE.json configs[2])")
         self.input_names = ("src", "tgt", "src_logits", "tgt_logits")
         self.hbm_stage, self.hbm_kernel = "softmax_em", "softmax_moments16_kernel"
-        self.stage_kernels = {"knn_edge": "knn3 kernel (distance + top-k + edge write)", "softmax_em": self.hbm_kernel,
+        self.stage_kernels = {"knn_edge": "knn3_select_kernel<20> (distance + top-k + edge write)", "softmax_em": self.hbm_kernel,
                               "gmm_register": "gmm_register_kernel"}
 
     def host_inputs(self, first, pairs, distinct):
