@@ -227,10 +227,11 @@ class Flagship:
         return out
 
     def launches(self):
-        out = {"knn_edge": 2, "cluster": 2, "feat_moments": 2, "procrustes": 1}
-        if self.C:
-            out["knn_wide"] = 2
-        return out
+        """Kernel launches per step and stage (both clouds).  cfg 4: the tiled kNN is a pre-pass + the sweep, the tensor-core
+        kNN an operand pre-kernel + the pipeline kernel, the feature M-step in split mode the partial kernel + the fold."""
+        if self.cfg == 4:
+            return {"knn_edge": 4, "knn_wide": 4, "cluster": 2, "feat_moments": 4, "procrustes": 1}
+        return {"knn_edge": 2, "cluster": 2, "feat_moments": 2, "procrustes": 1}
 
     def gpu_step(self, d, timers=None, overlap=True):
         from ogmm_b200 import pipeline
