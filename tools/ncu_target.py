@@ -31,3 +31,13 @@ if what == "wide":
     for _ in range(reps):
         ops.knn_graph(xw, xw, 20)
     torch.cuda.synchronize()
+if what in ("tiles", "dsmem"):
+    big, _, _, _ = synth.modelnet_batch(0, 4, 16384)
+    xb = torch.from_numpy(big).cuda().transpose(1, 2)                  # (4,16384,3) view, the cfg 4 clouds
+    ob = torch.sigmoid(torch.randn(4, 16384, generator=torch.Generator().manual_seed(1))).cuda()
+    for _ in range(reps):
+        if what == "tiles":
+            ops.knn_graph(xb, xb, 20, want_edge=True)
+        else:
+            ops.sinkhorn_cluster(xb, ob, 64)
+    torch.cuda.synchronize()
